@@ -1,0 +1,81 @@
+"""Shared parity inputs, all small enough for seconds on CPU."""
+import numpy as np
+
+from tilespmv_b200 import generators as g
+
+
+def _unsorted(case):
+    """Same matrix with the columns of every row reversed: exercises 'in-tile order is input order'."""
+    m, n, rp, ci, v = case
+    ci2, v2 = ci.copy(), v.copy()
+    for i in range(m):
+        lo, hi = rp[i], rp[i + 1]
+        ci2[lo:hi] = ci[lo:hi][::-1]
+        v2[lo:hi] = v[lo:hi][::-1]
+    return m, n, rp, ci2, v2
+
+
+def _ragged(case, rowA, colA):
+    """Crop to rowA x colA (not multiples of 16): partial last block row / tile column."""
+    m, n, rp, ci, v = case
+    keep = np.zeros(len(ci), bool)
+    new_rp = np.zeros(rowA + 1, np.int32)
+    for i in range(rowA):
+        sel = ci[rp[i]:rp[i + 1]] < colA
+        keep[rp[i]:rp[i + 1]] = sel
+        new_rp[i + 1] = new_rp[i] + sel.sum()
+    return rowA, colA, new_rp, ci[keep], v[keep]
+
+
+def _empty_rows(m=64, n=64):
+    """Only rows 17 and 40 populated; whole block rows and the matrix tail are empty."""
+    rp = np.zeros(m + 1, np.int32)
+    cols, vals = [], []
+    for i in range(m):
+        if i == 17:
+            cols += [0, 5, 33, 63]
+        if i == 40:
+            cols += list(range(16, 48))
+        rp[i + 1] = len(cols)
+    return m, n, rp, np.array(cols, np.int32), (np.arange(len(cols)) % 10).astype(np.float64)
+
+
+CASES = {
+    "seven_formats": lambda: g.seven_formats(),
+    "lap2d_64": lambda: g.lap2d(64, val_mode=1),
+    "lap3d27_24": lambda: g.lap3d27(24, val_mode=1),
+    "banded_8k": lambda: g.banded(8192, val_mode=1),
+    "banded_8k_real": lambda: g.banded(8192, val_mode=0),
+    "band_contig_8k": lambda: g.band_contig(8192, val_mode=1),
+    "rmat_12": lambda: g.rmat(12, val_mode=1),
+    "rmat_12_real": lambda: g.rmat(12, val_mode=0),
+    "uniform_8k": lambda: g.uniform(8192, val_mode=1),
+    "banded_2k_real": lambda: g.banded(2048, val_mode=0),
+    "rmat_10_real": lambda: g.rmat(10, val_mode=0),
+    "uniform_2k": lambda: g.uniform(2048, val_mode=1),
+    "band_unsorted": lambda: _unsorted(g.band_contig(2048, hb=20, val_mode=0)),
+    "rmat_unsorted": lambda: _unsorted(g.rmat(10, val_mode=0)),
+    "ragged_band": lambda: _ragged(g.band_contig(1024, hb=18, val_mode=0), 1003, 1001),
+    "ragged_seven": lambda: _ragged(g.seven_formats(), 29, 37),
+    "ragged_rmat": lambda: _ragged(g.rmat(10, val_mode=1), 1000, 999),
+    "empty_rows": _empty_rows,
+    "empty_matrix": lambda: (32, 32, np.zeros(33, np.int32), np.zeros(0, np.int32), np.zeros(0)),
+    "dense_48": lambda: g.band_contig(48, hb=48, val_mode=0),
+}
+
+# larger inputs: used by the oracle-vs-reference test (CPU) and the full-size GPU tests
+BIG_CASES = {
+    "lap2d_256": lambda: g.lap2d(256, val_mode=1),
+    "lap3d27_48": lambda: g.lap3d27(48, val_mode=1),
+    "banded_64k": lambda: g.banded(65536, val_mode=0),
+    "band_contig_64k": lambda: g.band_contig(65536, val_mode=1),
+    "rmat_15": lambda: g.rmat(15, val_mode=0),
+    "uniform_64k": lambda: g.uniform(65536, val_mode=1),
+}
+
+
+def x_for(n, mode, dtype=np.float64, seed=7):
+    """mode 1: x[i] = i % 10 like main.cu:93-97; mode 0: seeded uniform(-1,1)."""
+    if mode == 1:
+        return (np.arange(n) % 10).astype(dtype)
+    return np.random.default_rng(seed).uniform(-1, 1, n).astype(dtype)
