@@ -1,0 +1,319 @@
+/*
+ * tilespmv.h -- C-ABI of the B200-native TileSpMV (libtilespmv_b200.so).
+ *
+ * Drop-in boundary for the hot path of SuperScientificSoftwareLaboratory/TileSpMV.  The reference
+ * has no library: its "API" is a set of C functions defined in headers and included once into
+ * src/main.cu (main.cu:1-7).  This header re-declares that surface -- the Tile_matrix struct and
+ * the three entry points the driver calls -- as exported symbols, and adds the plan/handle API
+ * the reference lacks (repeated SpMV on device-resident data, multi-GPU row blocks).
+ *
+ *   reference (file:line)                              this library
+ *   -------------------------------------------------  ------------------------------------------
+ *   struct Tile_matrix            format.h:3-56        Tile_matrix_f64 / Tile_matrix_f32
+ *   Tile_create                   csr2tile.h:629-635   Tile_create_f64 / _f32   (GPU conversion)
+ *   Tile_destroy                  format.h:58-94       Tile_destroy_f64 / _f32  (frees everything)
+ *   tilespmv_cpu (schedule part)  tilespmv_cpu.h:68-118, :142-257
+ *                                                      tilespmv_prepare_f64 / _f32 (ptroffset1/2 +
+ *                                                      warp-chunk schedule; NO CPU SpMV: the
+ *                                                      product has no CPU fallback)
+ *   call_tilespmv_cuda            tilespmv_cuda.h:794-809
+ *                                                      call_tilespmv_cuda_f64 / _f32
+ *   compile-time constants        common.h:12-63       TILESPMV_* macros below
+ *
+ * Precision is a compile-time macro in the reference (MAT_VAL_TYPE, common.h:12-14; float via
+ * -D, Makefile:5,22), so a shared library has to export two symbol sets.  Source-level drop-in:
+ * compile the caller with -DMAT_VAL_TYPE=double|float and include this header; the unsuffixed
+ * reference names then map to the matching set (bottom of this file).
+ *
+ * All functions are thread-compatible (one plan per host thread), keep no hidden global state
+ * besides a thread-local last-error string, and use the CUDA device current on the calling
+ * thread (the reference selects it with cudaSetDevice in main.cu:74).
+ * No torch / C++ types appear in any signature.
+ */
+#ifndef TILESPMV_H
+#define TILESPMV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- constants that are part of the format contract (common.h:12-63) ---- */
+#define TILESPMV_BLOCK_SIZE 16      /* BLOCK_SIZE        */
+#define TILESPMV_COO_NNZ_TH 12      /* COO_NNZ_TH        */
+#define TILESPMV_PREFETCH_SMEM_TH 4 /* PREFETCH_SMEM_TH  */
+#define TILESPMV_NUM_F 240          /* num_f (0xF0)      */
+#define TILESPMV_NUM_B 15           /* num_b (0x0F)      */
+#define TILESPMV_BENCH_REPEAT 1000  /* BENCH_REPEAT      */
+#define TILESPMV_WARMUP_NUM 200     /* WARMUP_NUM        */
+
+/* tile format codes stored in Tile_matrix.Format (csr2tile.h:154,162,193,235,272,310,319) */
+#define TILESPMV_FMT_CSR 0
+#define TILESPMV_FMT_COO 1
+#define TILESPMV_FMT_ELL 2
+#define TILESPMV_FMT_HYB 3
+#define TILESPMV_FMT_DENSE 4
+#define TILESPMV_FMT_DENSEROW 5
+#define TILESPMV_FMT_DENSECOL 6
+
+/* ---- status codes (0 = ok, negative = error; cf. ANONYMOUSLIB_* in CSR5 detail/common.h:13-18) ---- */
+#define TILESPMV_OK 0
+#define TILESPMV_ERR_INVALID (-1)     /* bad argument / inconsistent sizes            */
+#define TILESPMV_ERR_CUDA (-2)        /* a CUDA runtime call or kernel failed         */
+#define TILESPMV_ERR_ALLOC (-3)       /* host or device allocation failed             */
+#define TILESPMV_ERR_UNSUPPORTED (-4) /* e.g. sizes that overflow the int-indexed format */
+#define TILESPMV_ERR_NODEVICE (-5)    /* no CUDA device: there is NO CPU fallback     */
+#define TILESPMV_ERR_IO (-6)
+
+/* ---- Tile_matrix: field-for-field the reference struct (format.h:3-56) ---- */
+#define TILESPMV_DECLARE_TILE_MATRIX(NAME, VAL_T)                                               \
+    typedef struct                                                                              \
+    {                                                                                           \
+        int tilem;                                                                              \
+        int tilen;                                                                              \
+        int tilenum;                                                                            \
+        int *tile_ptr;                 /* [tilem+1]  level-1 CSR of tiles                     */ \
+        int *tile_columnidx;           /* [tilenum]  ascending inside a block row             */ \
+        int *tile_nnz;                 /* [tilenum+1] exclusive prefix of true nnz            */ \
+        char *Format;                  /* [tilenum]  TILESPMV_FMT_*                           */ \
+        int *blknnz;                   /* [tilenum+1] exclusive prefix of stored slots        */ \
+        unsigned char *blknnznnz;      /* [tilenum+1] per-tile slots, wrapped to 8 bits       */ \
+        int *dnsrowptr;                /* [tilenum+1]                                         */ \
+        int *dnscolptr;                /* [tilenum+1]                                         */ \
+        char *tilewidth;               /* [tilenum]  ELL / HYB width                          */ \
+        int *csr_offset;               /* [tilenum+1] prefix offsets into the per-format arrays */ \
+        int *csrptr_offset;                                                                     \
+        int *coo_offset;                                                                        \
+        int *ell_offset;                                                                        \
+        int *hyb_offset;                                                                        \
+        int *hyb_coocount;                                                                      \
+        int *dns_offset;                                                                        \
+        int *dnsrow_offset;                                                                     \
+        int *dnscol_offset;                                                                     \
+        int *new_coocount;                                                                      \
+        VAL_T *Blockcsr_Val;                                                                    \
+        unsigned char *Blockcsr_Ptr;                                                            \
+        unsigned char *csr_compressedIdx;                                                       \
+        int csrsize;                                                                            \
+        int csrptrlen;                                                                          \
+        VAL_T *Blockcoo_Val;                                                                    \
+        unsigned char *coo_compressed_Idx;                                                      \
+        int coosize;                                                                            \
+        VAL_T *Blockell_Val;                                                                    \
+        unsigned char *ell_compressedIdx;                                                       \
+        int ellsize;                                                                            \
+        VAL_T *Blockhyb_Val;                                                                    \
+        unsigned char *hybIdx;                                                                  \
+        int hybsize;                                                                            \
+        int hybellsize;                                                                         \
+        int hybcoosize;                                                                         \
+        VAL_T *Blockdense_Val;                                                                  \
+        int dnssize;                                                                            \
+        VAL_T *Blockdenserow_Val;                                                               \
+        char *denserowid;                                                                       \
+        int dnsrowsize;                                                                         \
+        VAL_T *Blockdensecol_Val;                                                               \
+        char *densecolid;                                                                       \
+        int dnscolsize;                                                                         \
+        int coototal;                                                                           \
+        VAL_T *deferredcoo_val;        /* side CSR of the very sparse (COO) tiles             */ \
+        int *deferredcoo_colidx;       /* GLOBAL columns, ascending inside a row              */ \
+        int *deferredcoo_ptr;          /* [rowA+1]                                            */ \
+    } NAME
+
+TILESPMV_DECLARE_TILE_MATRIX(Tile_matrix_f64, double);
+TILESPMV_DECLARE_TILE_MATRIX(Tile_matrix_f32, float);
+
+/* =============================== drop-in entry points =================================== */
+
+/*
+ * Tile_create (csr2tile.h:629-635).  Same contract: the caller allocates the struct and keeps
+ * ownership of the (host) CSR arrays; every array in the struct is malloc'ed here; rowA / colA
+ * need not be multiples of 16; prints "\n  The number of tile = %i\n" like the reference (:661).
+ * The conversion itself runs on the GPU (tile discovery, format selection, scatter, nibble
+ * packing, side-CSR extraction) and the result is bit-exact with the reference CPU conversion.
+ * The reference returns void and has no error path; on failure this leaves tilenum = -1 and the
+ * reason in tilespmv_last_error().
+ */
+void Tile_create_f64(Tile_matrix_f64 *matrix, int rowA, int colA, int nnzA, int *csrRowPtrA,
+                     int *csrColIdxA, double *csrValA);
+void Tile_create_f32(Tile_matrix_f32 *matrix, int rowA, int colA, int nnzA, int *csrRowPtrA,
+                     int *csrColIdxA, float *csrValA);
+
+/* Tile_destroy (format.h:58-94): frees every array (the reference leaks four) and zeroes the
+ * struct; like the reference it does not free the struct itself. */
+void Tile_destroy_f64(Tile_matrix_f64 *matrix);
+void Tile_destroy_f32(Tile_matrix_f32 *matrix);
+
+/*
+ * The bookkeeping half of tilespmv_cpu (tilespmv_cpu.h:68-118 and the ptroffset writes at
+ * :142-257): fills the caller-allocated ptroffset1/2[tilenum] and returns the warp-chunk
+ * schedule through malloc'ed arrays (caller frees with free()).  The reference routes these
+ * through its CPU SpMV; this library needs none of them (call_tilespmv_cuda below ignores them)
+ * but they stay derivable for callers and parity tests.  Returns a status code.
+ */
+int tilespmv_prepare_f64(const Tile_matrix_f64 *matrix, int *ptroffset1, int *ptroffset2,
+                         int *rowblkblock, unsigned int **blkcoostylerowidx,
+                         int **blkcoostylerowidx_colstart, int **blkcoostylerowidx_colstop, int rowA);
+int tilespmv_prepare_f32(const Tile_matrix_f32 *matrix, int *ptroffset1, int *ptroffset2,
+                         int *rowblkblock, unsigned int **blkcoostylerowidx,
+                         int **blkcoostylerowidx_colstart, int **blkcoostylerowidx_colstop, int rowA);
+
+/*
+ * call_tilespmv_cuda (tilespmv_cuda.h:794-809).  All pointers are HOST pointers; the callee owns
+ * every device allocation for the duration of the call; y[rowA] receives A*x; alpha is accepted
+ * and ignored exactly like the reference (csr5_spmv_cuda.h:22); ptroffset*, the schedule arrays,
+ * csr* and y_golden are accepted for signature compatibility and unused.  Follows the reference
+ * protocol: WARMUP_NUM warm-ups then BENCH_REPEAT timed SpMVs (CUDA events around the batch),
+ * prints "  CUDA SpMV runtime %4.2f ms, %4.2f GFlops\n\n" (:1139) and appends
+ * "filename,rowA,colA,nnzA,ms,gflops" to ./results.csv (:1142-1147).
+ * TILESPMV_BENCH_REPEAT / TILESPMV_WARMUP_NUM environment variables override the counts.
+ * The reference returns void; errors are reported through tilespmv_last_error() and y is left
+ * untouched.
+ */
+void call_tilespmv_cuda_f64(char *filename, Tile_matrix_f64 *matrix, int *ptroffset1, int *ptroffset2,
+                            int rowblkblock, unsigned int *blkcoostylerowidx,
+                            int *blkcoostylerowidx_colstart, int *blkcoostylerowidx_colstop, int rowA,
+                            int colA, int nnzA, int *csrRowPtrA, int *csrColIdxA, double *csrValA,
+                            double alpha, double *x, double *y, double *y_golden);
+void call_tilespmv_cuda_f32(char *filename, Tile_matrix_f32 *matrix, int *ptroffset1, int *ptroffset2,
+                            int rowblkblock, unsigned int *blkcoostylerowidx,
+                            int *blkcoostylerowidx_colstart, int *blkcoostylerowidx_colstop, int rowA,
+                            int colA, int nnzA, int *csrRowPtrA, int *csrColIdxA, float *csrValA,
+                            float alpha, float *x, float *y, float *y_golden);
+
+/* ================================ handle / plan API ====================================== */
+
+/* a Tile_matrix resident in device memory (opaque) */
+typedef struct tilespmv_dmat tilespmv_dmat;
+/* a packed, scheduled SpMV plan for one dmat on one GPU (opaque) */
+typedef struct tilespmv_plan tilespmv_plan;
+
+#define TILESPMV_F64 8
+#define TILESPMV_F32 4
+
+/* flags of tilespmv_convert */
+#define TILESPMV_CSR_ON_DEVICE 1 /* rowptr / colidx / val are device pointers */
+
+/*
+ * GPU csr2tile: CSR (host pointers, or device pointers with TILESPMV_CSR_ON_DEVICE) -> a
+ * device-resident Tile_matrix.  precision is TILESPMV_F64 or TILESPMV_F32 and tells the type
+ * behind val.  Rows >= rowA present in rowptr are ignored (the reference driver truncates rowA to
+ * a multiple of 16 and keeps the CSR arrays, main.cu:71).
+ */
+int tilespmv_convert(int precision, int rowA, int colA, const int *rowptr, const int *colidx,
+                     const void *val, unsigned flags, tilespmv_dmat **out);
+/* upload an existing host Tile_matrix (e.g. one produced by the reference's CPU Tile_create) */
+int tilespmv_dmat_upload_f64(const Tile_matrix_f64 *matrix, int rowA, int colA, tilespmv_dmat **out);
+int tilespmv_dmat_upload_f32(const Tile_matrix_f32 *matrix, int rowA, int colA, tilespmv_dmat **out);
+/* download into a caller-allocated struct; arrays are malloc'ed (free with Tile_destroy_*) */
+int tilespmv_dmat_export_f64(const tilespmv_dmat *dm, Tile_matrix_f64 *matrix);
+int tilespmv_dmat_export_f32(const tilespmv_dmat *dm, Tile_matrix_f32 *matrix);
+void tilespmv_dmat_destroy(tilespmv_dmat *dm);
+
+typedef struct
+{
+    int precision;        /* TILESPMV_F64 / TILESPMV_F32 */
+    int rowA, colA;
+    int tilem, tilen, tilenum;
+    int64_t nnz;          /* true nonzeros */
+    int64_t nnz_side;     /* coototal: nonzeros served from the extracted side CSR */
+    int64_t tiles_by_format[7];
+    int64_t device_bytes; /* bytes of device memory held by the dmat */
+} tilespmv_dmat_info;
+int tilespmv_dmat_get_info(const tilespmv_dmat *dm, tilespmv_dmat_info *info);
+
+typedef struct
+{
+    int chunk_bytes;  /* max bytes of one scheduler chunk of the packed stream (0 = default) */
+    int xstage_bytes; /* max bytes of x staged in shared memory per chunk (0 = default)      */
+    int ctas_per_sm;  /* persistent CTAs per SM (0 = default)                                */
+    int reserved[5];
+} tilespmv_plan_options;
+
+/* Packs the tiles into the 16-byte-aligned per-chunk stream and builds the persistent,
+ * byte-balanced chunk schedule.  opts may be NULL. */
+int tilespmv_plan_create(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tilespmv_plan **out);
+void tilespmv_plan_destroy(tilespmv_plan *plan);
+
+/* y = A*x with DEVICE pointers (16-byte aligned), asynchronous on `stream` (a cudaStream_t
+ * passed as void*; NULL = default stream).  x has colA entries, y has rowA entries. */
+int tilespmv_plan_spmv(tilespmv_plan *plan, const void *d_x, void *d_y, void *stream);
+/* y = A*x with HOST pointers: H2D of x, the SpMV, D2H of y, synchronous (the end-to-end path). */
+int tilespmv_plan_spmv_host(tilespmv_plan *plan, const void *x, void *y);
+
+/*
+ * Multi-GPU repeated SpMV (row-block sharding, x replicated): after computing its rows the
+ * kernel also stores them straight into x_next of every peer (P2P-mapped pointers over NVLink)
+ * at row_offset, so the all-gather of the next x is the kernel's own store stream.
+ * peer_x[i] (i < npeers) are device pointers valid on THIS device (cudaIpcOpenMemHandle /
+ * peer access enabled by the caller); pass npeers = 0 to switch the fused epilogue off.
+ */
+int tilespmv_plan_set_peers(tilespmv_plan *plan, int npeers, void *const *peer_x, int64_t row_offset);
+
+typedef struct
+{
+    int precision;
+    int64_t nchunks;           /* scheduler chunks                                        */
+    int64_t stream_bytes;      /* bytes of the packed stream read by one SpMV             */
+    int64_t algorithmic_bytes; /* B_alg of SURVEY.md 8(d) for this matrix                 */
+    int64_t csr_bytes;         /* B_csr (cross-format comparison figure)                  */
+    int64_t split_rows;        /* block rows cut across chunks (fixed up by a 2nd launch) */
+    int launches_per_spmv;     /* kernels launched by one tilespmv_plan_spmv              */
+    int grid, block, smem_bytes;
+    int chunk_bytes, xstage_bytes;
+    int64_t device_bytes;
+} tilespmv_plan_info;
+int tilespmv_plan_get_info(const tilespmv_plan *plan, tilespmv_plan_info *info);
+
+/* Time `iters` back-to-back SpMVs on device buffers with CUDA events on `stream` (after
+ * `warmup` untimed ones); returns mean milliseconds per SpMV in *ms_per_spmv. */
+int tilespmv_plan_time(tilespmv_plan *plan, const void *d_x, void *d_y, int warmup, int iters,
+                       void *stream, double *ms_per_spmv);
+
+/* Matrix Market front end with the semantics of mmio_allinone (mmio_highlevel.h:593-759):
+ * returns 0 / -1 (open) / -2 (banner) / -4 (size line); outputs malloc'ed, caller frees. */
+int tilespmv_mmio_allinone_f64(int *m, int *n, int *nnz, int *isSymmetric, int **csrRowPtr,
+                               int **csrColIdx, double **csrVal, const char *filename);
+int tilespmv_mmio_allinone_f32(int *m, int *n, int *nnz, int *isSymmetric, int **csrRowPtr,
+                               int **csrColIdx, float **csrVal, const char *filename);
+
+/* last error message of the calling thread ("" if none) and library version */
+const char *tilespmv_last_error(void);
+const char *tilespmv_version(void);
+/* number of CUDA kernels this library has launched in this process (instrumentation) */
+int64_t tilespmv_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+/* ---- source-level drop-in: the reference's unsuffixed names (format.h, csr2tile.h, ...) ---- */
+#ifdef TILESPMV_REFERENCE_NAMES
+#ifndef MAT_VAL_TYPE
+#define MAT_VAL_TYPE double
+#endif
+#ifndef MAT_PTR_TYPE
+#define MAT_PTR_TYPE int
+#endif
+#ifndef BLOCK_SIZE
+#define BLOCK_SIZE TILESPMV_BLOCK_SIZE
+#endif
+#define TILESPMV_CAT_(a, b) a##b
+#define TILESPMV_CAT(a, b) TILESPMV_CAT_(a, b)
+#ifdef TILESPMV_USE_F32
+#define TILESPMV_SUFFIX _f32
+#else
+#define TILESPMV_SUFFIX _f64
+#endif
+#define Tile_matrix TILESPMV_CAT(Tile_matrix, TILESPMV_SUFFIX)
+#define Tile_create TILESPMV_CAT(Tile_create, TILESPMV_SUFFIX)
+#define Tile_destroy TILESPMV_CAT(Tile_destroy, TILESPMV_SUFFIX)
+#define call_tilespmv_cuda TILESPMV_CAT(call_tilespmv_cuda, TILESPMV_SUFFIX)
+#define tilespmv_prepare TILESPMV_CAT(tilespmv_prepare, TILESPMV_SUFFIX)
+#define mmio_allinone TILESPMV_CAT(tilespmv_mmio_allinone, TILESPMV_SUFFIX)
+#endif
+
+#endif /* TILESPMV_H */

@@ -1,0 +1,100 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/tilespmv.h
+declares, and refuses to compute without a GPU (no CPU fallback).  No kernels are launched."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tilespmv_b200 import _capi, api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "tilespmv.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = src[:src.index("#ifdef TILESPMV_REFERENCE_NAMES")]
+    names = set(re.findall(r"\b((?:Tile_|call_tilespmv_|tilespmv_)[A-Za-z0-9_]+)\s*\(", src))
+    return sorted(n for n in names if not n.startswith("tilespmv_dmat ") and n not in ("tilespmv_dmat", "tilespmv_plan"))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _capi.load()
+    declared = _declared_functions()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/tilespmv.h but not exported"
+    assert set(declared) == set(_capi.EXPORTS)
+    assert b"sm_100a" in L.tilespmv_version()
+
+
+def test_struct_layout_matches_header():
+    # 3 ints + 47 pointer/int fields, natural alignment: the struct the reference's main.cu mallocs
+    assert C.sizeof(_capi.TileMatrixF64) == C.sizeof(_capi.TileMatrixF32)
+    assert [f[0] for f in _capi.TileMatrixF64._fields_][:7] == ["tilem", "tilen", "tilenum", "tile_ptr",
+                                                                 "tile_columnidx", "tile_nnz", "Format"]
+    assert len(_capi.TileMatrixF64._fields_) == 50
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback_without_gpu():
+    rp = np.array([0, 1, 2], np.int32)
+    ci = np.array([0, 1], np.int32)
+    v = np.array([1.0, 2.0])
+    with pytest.raises(api.TileSpMVError) as e:
+        api.DeviceTileMatrix.from_csr(2, 2, rp, ci, v)
+    assert "no CPU fallback" in str(e.value)
+    with pytest.raises(api.TileSpMVError):
+        api.Tile_create(2, 2, rp, ci, v)
+
+
+def test_prepare_is_host_bookkeeping_only():
+    """tilespmv_prepare on a Tile_matrix built by the oracle equals the golden ptroffset/schedule."""
+    from oracle import oracle_py as O
+    from tests import golden_util as G
+    for path in G.golden_files("f64"):
+        d = G.load(path)
+        m, n = (int(v) for v in d["in_shape"])
+        ora = O.Oracle("f64")
+        Mo = ora.tile_create(m, n, d["in_rowptr"], d["in_colidx"], d["in_val"])
+        M = api.HostTileMatrix(api.F64, m, n)
+        C.memmove(C.byref(M.struct), C.byref(Mo), C.sizeof(Mo))  # borrow the oracle's arrays
+        p1, p2, rbb, a, b, c = api.tilespmv_prepare(M, m)
+        assert np.array_equal(p1, d["ptroffset1"]) and np.array_equal(p2, d["ptroffset2"])
+        assert rbb == int(d["rowblkblock"][0])
+        assert np.array_equal(a, d["blkcoostylerowidx"])
+        assert np.array_equal(b, d["blkcoostylerowidx_colstart"])
+        assert np.array_equal(c, d["blkcoostylerowidx_colstop"])
+        ora.tile_destroy(Mo)
+
+
+def test_mmio_front_end_matches_oracle(tmp_path):
+    from oracle import oracle_py as O
+    from tilespmv_b200 import generators as g
+    m, n, rp, ci, v = g.banded(300, val_mode=0)
+    p1 = str(tmp_path / "a.mtx")
+    g.write_mtx(p1, m, n, rp, ci, v)
+    p2 = str(tmp_path / "s.mtx")
+    with open(p2, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate integer symmetric\n%c\n6 6 5\n1 1 3\n3 1 -2\n5 2 7\n4 4 1\n6 1 9\n")
+    for p in (p1, p2):
+        rc, got = api.mmio_allinone(p)
+        rco, want = O.Oracle("f64").mtx_read(p)
+        assert rc == rco == 0
+        assert got[:3] == want[:3]
+        for a, b in zip(got[3:], want[3:]):
+            assert a.tobytes() == b.tobytes()
+    assert api.mmio_allinone(str(tmp_path / "nope.mtx"))[0] == -1
+    bad = str(tmp_path / "bad.mtx")
+    open(bad, "w").write("hello world\n1 1 1\n")
+    assert api.mmio_allinone(bad)[0] == -2

@@ -1,0 +1,177 @@
+"""GPU parity tests (run with -m gpu on a B200): every call goes through the C-ABI of
+libtilespmv_b200.so; the oracle (oracle/) is only the checker.
+
+  * Tile_create on the GPU is BIT-EXACT with the reference conversion (all Tile_matrix arrays)
+  * y = A*x matches tilespmv_cpu: bit-exact on the reference driver's integer data
+    (val = j%10, x = i%10, main.cu:68-69,93-97), and within 1e-12 (fp64) / 1e-5 (fp32) of
+    sum_j |a_ij||x_j| on seeded uniform(-1,1) data -- the tolerance BASELINE.json states
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle_py as O
+from tests import golden_util as G
+from tests.cases import BIG_CASES, CASES, x_for
+from tilespmv_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"f64": 1e-12, "f32": 1e-5}
+
+
+def _prec(precision):
+    return api.F64 if precision == "f64" else api.F32
+
+
+def assert_y_close(y, y_ref, scale, precision, what=""):
+    tol = TOL[precision]
+    err = np.abs(y.astype(np.float64) - y_ref.astype(np.float64))
+    bound = tol * np.maximum(scale.astype(np.float64), np.finfo(np.float64).tiny)
+    bad = np.flatnonzero(err > bound)
+    assert len(bad) == 0, (f"{what}: {len(bad)} rows out of tolerance, first {bad[:8]}, got {y[bad[:8]]}, "
+                           f"want {y_ref[bad[:8]]}")
+
+
+def check_matrix(case, precision, plan_kwargs=None, exact_modes=(1,), real_modes=(0,)):
+    m, n, rp, ci, v = case
+    ora = O.Oracle(precision)
+    v = v.astype(ora.val_dtype)
+    Mo = ora.tile_create(m, n, rp, ci, v)
+    want = ora.arrays(Mo, m)
+    # --- conversion on the GPU, bit-exact ---
+    dm = api.DeviceTileMatrix.from_csr(m, n, rp, ci, v)
+    Mg = dm.export()
+    G.assert_tile_arrays_equal(Mg.arrays(), want, "Tile_matrix.")
+    info = dm.info()
+    assert info.tilenum == Mo.tilenum and info.nnz == int(rp[m]) and info.nnz_side == Mo.coototal
+    assert list(info.tiles_by_format) == [int((want["Format"] == f).sum()) for f in range(7)]
+    # --- SpMV ---
+    plan = api.Plan(dm, **(plan_kwargs or {}))
+    integer_vals = bool(np.all(v == np.round(v)))
+    for mode in exact_modes + real_modes:
+        x = x_for(n, mode, ora.val_dtype)
+        y_ref, _, _ = ora.tilespmv_cpu(Mo, m, n, x)
+        y = plan.spmv_host(x)
+        if mode == 1 and integer_vals and (precision == "f64" or np.abs(y_ref).max(initial=0) < 2 ** 24):
+            assert y.tobytes() == y_ref.tobytes(), f"integer data must be bit-exact (mode {mode})"
+        scale = ora.csr_abs_spmv(m, rp, ci, v, x)
+        assert_y_close(y, y_ref, scale, precision, f"mode {mode}")
+    pi = plan.info()
+    plan.destroy()
+    dm.destroy()
+    Mg.destroy()
+    ora.tile_destroy(Mo)
+    return pi
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_convert_and_spmv_f64(name):
+    check_matrix(CASES[name](), "f64")
+
+
+@pytest.mark.parametrize("name", ["seven_formats", "lap2d_64", "banded_8k_real", "rmat_12_real", "ragged_band",
+                                  "band_unsorted", "ragged_seven", "uniform_8k", "dense_48"])
+def test_convert_and_spmv_f32(name):
+    check_matrix(CASES[name](), "f32")
+
+
+@pytest.mark.parametrize("name", sorted(BIG_CASES))
+def test_convert_and_spmv_big(name):
+    pi = check_matrix(BIG_CASES[name](), "f64")
+    assert pi.nchunks > 0 and pi.stream_bytes > 0
+
+
+@pytest.mark.parametrize("name", ["seven_formats", "rmat_12", "band_contig_8k", "uniform_8k", "lap3d27_24",
+                                  "ragged_rmat"])
+@pytest.mark.parametrize("cfg", [dict(chunk_bytes=2560, xstage_bytes=128), dict(chunk_bytes=2560, xstage_bytes=256),
+                                 dict(chunk_bytes=8192, xstage_bytes=4096), dict(chunk_bytes=4096, xstage_bytes=3072, ctas_per_sm=1)])
+def test_chunk_configurations_and_split_rows(name, cfg):
+    """Tiny x-staging budgets force block rows to be cut into pieces (scratch + fix-up kernel)."""
+    pi = check_matrix(CASES[name](), "f64", plan_kwargs=cfg)
+    if cfg["xstage_bytes"] == 128 and name in ("rmat_12", "band_contig_8k", "uniform_8k", "lap3d27_24"):
+        assert pi.split_rows > 0 and pi.launches_per_spmv == 2
+
+
+@pytest.mark.parametrize("path", G.golden_files(), ids=os.path.basename)
+def test_golden_fixtures_through_the_drop_in_entry_points(path):
+    """Tile_create -> tilespmv_prepare -> call_tilespmv_cuda exactly as main.cu:87-180 calls them,
+    checked against fixtures produced by the unmodified reference CPU path."""
+    d = G.load(path)
+    m, n = (int(v) for v in d["in_shape"])
+    os.environ["TILESPMV_BENCH_REPEAT"] = "3"
+    os.environ["TILESPMV_WARMUP_NUM"] = "1"
+    cwd = os.getcwd()
+    M = api.Tile_create(m, n, d["in_rowptr"], d["in_colidx"], d["in_val"])
+    G.assert_tile_arrays_equal(M.arrays(), G.tile_arrays(d), d["name"] + ":")
+    p1, p2, rbb, a, b, c = api.tilespmv_prepare(M, m)
+    assert np.array_equal(p1, d["ptroffset1"]) and np.array_equal(p2, d["ptroffset2"])
+    assert rbb == int(d["rowblkblock"][0]) and np.array_equal(a, d["blkcoostylerowidx"])
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            y = api.call_tilespmv_cuda("golden.mtx", M, m, n, int(d["in_rowptr"][m]), d["x"])
+            rows = open("results.csv").read().strip().split("\n")
+        finally:
+            os.chdir(cwd)
+    assert rows[-1].startswith(f"golden.mtx,{m},{n},{int(d['in_rowptr'][m])},")
+    if d["precision"] == "f64" and np.all(d["in_val"] == np.round(d["in_val"])):
+        assert y.tobytes() == d["y"].tobytes()
+    else:
+        ora = O.Oracle(d["precision"])
+        scale = ora.csr_abs_spmv(m, d["in_rowptr"], d["in_colidx"], d["in_val"], d["x"])
+        assert_y_close(y, d["y"], scale, d["precision"], d["name"])
+    M.destroy()
+
+
+def test_upload_of_a_reference_built_tile_matrix():
+    """A Tile_matrix produced on the CPU (here: by the oracle) can be uploaded and multiplied."""
+    m, n, rp, ci, v = CASES["seven_formats"]()
+    ora = O.Oracle("f64")
+    Mo = ora.tile_create(m, n, rp, ci, v)
+    M = api.HostTileMatrix(api.F64, m, n)
+    C.memmove(C.byref(M.struct), C.byref(Mo), C.sizeof(Mo))
+    dm = api.DeviceTileMatrix.upload(M)
+    plan = api.Plan(dm)
+    x = x_for(n, 1)
+    y_ref, _, _ = ora.tilespmv_cpu(Mo, m, n, x)
+    assert plan.spmv_host(x).tobytes() == y_ref.tobytes()
+    ora.tile_destroy(Mo)
+
+
+def test_device_pointer_path_streams_and_linearity():
+    """tilespmv_plan_spmv on torch device buffers and a non-default stream; A(ax+by) = aAx + bAy."""
+    import torch
+    m, n, rp, ci, v = BIG_CASES["lap3d27_48"]()
+    dm = api.DeviceTileMatrix.from_csr(m, n, rp, ci, v)
+    plan = api.Plan(dm)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    x1 = torch.randint(-8, 9, (n,), generator=g).double().cuda()
+    x2 = torch.randint(-8, 9, (n,), generator=g).double().cuda()
+    y1, y2, y3 = (torch.full((m,), float("nan"), dtype=torch.float64, device="cuda") for _ in range(3))
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        plan.spmv(x1.data_ptr(), y1.data_ptr(), st.cuda_stream)
+        plan.spmv(x2.data_ptr(), y2.data_ptr(), st.cuda_stream)
+        x3 = 3 * x1 - 2 * x2
+        plan.spmv(x3.data_ptr(), y3.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    assert torch.equal(y3, 3 * y1 - 2 * y2)  # small integers: exact
+    # against torch's own CSR SpMV as an independent check
+    A = torch.sparse_csr_tensor(torch.from_numpy(rp).long(), torch.from_numpy(ci).long(),
+                                torch.from_numpy(v), size=(m, n)).cuda()
+    assert torch.equal(A @ x1, y1)
+    ms = plan.time(x1.data_ptr(), y1.data_ptr(), warmup=2, iters=5)
+    assert ms > 0
+    with pytest.raises(api.TileSpMVError):
+        plan.spmv(x1.data_ptr() + 8, y1.data_ptr())  # misaligned x
+
+
+def test_config1_lap2d_1024_against_oracle():
+    """BASELINE config 1: 2-D 5-point Laplacian 1024^2 through conversion + SpMV, full size."""
+    from tilespmv_b200 import generators as g
+    pi = check_matrix(g.lap2d(1024, val_mode=1), "f64")
+    assert pi.algorithmic_bytes == 67197320  # B_alg(C1) of SURVEY.md Appendix D

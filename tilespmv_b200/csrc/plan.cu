@@ -1,0 +1,613 @@
+// plan.cu -- builds the SpMV plan from a device-resident Tile_matrix:
+//   1. per-tile stream cost + prefix sums (device)
+//   2. byte-balanced chunking of block rows, long block rows cut into pieces (host, O(tilem))
+//   3. packing of every chunk into the 16-byte-aligned stream (device, one CTA per chunk)
+// This replaces what the reference does with a throw-away SpMV launch (stir_spmv_cuda_kernel_v5
+// recording per-warp COO replay lists, tilespmv_cuda.h:5-392, :1042-1056) and with the <=4-tile
+// warp chunks of tilespmv_cpu.h:68-118: chunks here are bounded by BYTES, not tile counts.
+#include <algorithm>
+
+#include "plan.cuh"
+#include "primitives.cuh"
+
+namespace tsp
+{
+
+constexpr int PL_THREADS = 256;
+constexpr int PACK_THREADS = 128;
+
+// ---------------------------------------------------------------------------------------------
+// 1. per-tile costs
+// ---------------------------------------------------------------------------------------------
+struct TileCostIn // 8 B descriptor + payload for tiles that live in the stream, 0 for COO tiles
+{
+    const char *fmt;
+    const int *tile_nnz;
+    const char *width;
+    const int *dnsrowptr, *dnscolptr;
+    int T;
+    uint32_t vs;
+    __device__ __forceinline__ int operator()(size_t i) const
+    {
+        if (i >= (size_t)T)
+            return 0;
+        const int f = fmt[i];
+        if (f == TILESPMV_FMT_COO)
+            return 0;
+        const int nd = f == TILESPMV_FMT_DENSEROW ? dnsrowptr[i + 1] - dnsrowptr[i]
+                                                  : (f == TILESPMV_FMT_DENSECOL ? dnscolptr[i + 1] - dnscolptr[i] : 0);
+        return 8 + (int)tile_payload_bytes(f, tile_nnz[i + 1] - tile_nnz[i], (int)width[i], nd, vs);
+    }
+};
+struct NonCooIn
+{
+    const char *fmt;
+    int T;
+    __device__ __forceinline__ int operator()(size_t i) const
+    {
+        return i < (size_t)T && fmt[i] != TILESPMV_FMT_COO ? 1 : 0;
+    }
+};
+
+__global__ void __launch_bounds__(PL_THREADS)
+    row_summary_kernel(int tilem, int rowA, const int *__restrict__ tile_ptr, const long long *__restrict__ pbscan,
+                       const int *__restrict__ ncscan, const int *__restrict__ side_ptr,
+                       long long *__restrict__ row_pay, int *__restrict__ row_nt, int *__restrict__ row_s0)
+{
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > tilem)
+        return;
+    int r0 = b * TS < rowA ? b * TS : rowA;
+    row_s0[b] = side_ptr[r0]; // side entries of block row b are [row_s0[b], row_s0[b+1])
+    if (b < tilem)
+    {
+        int t0 = tile_ptr[b], t1 = tile_ptr[b + 1];
+        row_pay[b] = pbscan[t1] - pbscan[t0]; // includes 8 B of descriptor per stream tile
+        row_nt[b] = ncscan[t1] - ncscan[t0];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. packing
+// ---------------------------------------------------------------------------------------------
+template <class T>
+struct PackArgs
+{
+    // plan tables
+    const PlanItem *items;
+    const long long *chunk_item0; // [nchunks+1]
+    const unsigned long long *chunk_off;
+    const long long *pbscan;
+    const int *ncscan;
+    unsigned char *stream;
+    int *error_flag;
+    // Tile_matrix (device)
+    int rowA, colA, tilem, tilen;
+    const int *tile_columnidx, *tile_nnz;
+    const char *Format, *tilewidth;
+    const int *csr_offset, *csrptr_offset, *ell_offset, *dns_offset, *dnsrow_offset, *dnscol_offset, *dnsrowptr,
+        *dnscolptr;
+    const T *Blockcsr_Val, *Blockell_Val, *Blockdense_Val, *Blockdenserow_Val, *Blockdensecol_Val;
+    const unsigned char *Blockcsr_Ptr, *csr_compressedIdx, *ell_compressedIdx;
+    const char *denserowid, *densecolid;
+    const int *side_ptr, *side_col;
+    const T *side_val;
+};
+
+__device__ __forceinline__ unsigned nib_global(const unsigned char *packed, int pos)
+{
+    unsigned b = packed[pos >> 1];
+    return (pos & 1) ? (b & 15u) : (b >> 4);
+}
+
+// writes descriptor + payload of tile t; runs in ONE thread (payloads are <= 2 KB)
+template <class T>
+__device__ void pack_tile(const PackArgs<T> &a, int t, int br, unsigned char *desc_out, unsigned char *pay)
+{
+    const int f = a.Format[t];
+    const int tc = a.tile_columnidx[t];
+    const int nnz = a.tile_nnz[t + 1] - a.tile_nnz[t];
+    const int rowlen = br == a.tilem - 1 ? a.rowA - (a.tilem - 1) * TS : TS;
+    const int collen = tc == a.tilen - 1 ? a.colA - (a.tilen - 1) * TS : TS;
+    uint32_t w = 0, aux = 0;
+    T *pv = reinterpret_cast<T *>(pay);
+    switch (f)
+    {
+    case TILESPMV_FMT_CSR:
+    {
+        const int o = a.csr_offset[t], po = a.csrptr_offset[t];
+        for (int r = 0; r < TS; r++)
+            pay[r] = r < rowlen ? a.Blockcsr_Ptr[po + r] : (unsigned char)nnz;
+        T *v = reinterpret_cast<T *>(pay + 16);
+        unsigned char *ix = pay + 16 + pad8((uint32_t)nnz * (uint32_t)sizeof(T));
+        for (int k = 0; k < nnz; k++)
+            v[k] = a.Blockcsr_Val[o + k];
+        for (int k = 0; k < nnz; k += 2)
+        {
+            unsigned hi = nib_global(a.csr_compressedIdx, o + k);
+            unsigned lo = k + 1 < nnz ? nib_global(a.csr_compressedIdx, o + k + 1) : 0u;
+            ix[k >> 1] = (unsigned char)((hi << 4) | lo);
+        }
+        aux = (uint32_t)nnz;
+        break;
+    }
+    case TILESPMV_FMT_ELL:
+    {
+        const int o = a.ell_offset[t];
+        w = (uint32_t)(unsigned char)a.tilewidth[t];
+        unsigned char *ix = pay + w * 16u * (uint32_t)sizeof(T);
+        for (uint32_t s = 0; s < w; s++)
+        {
+            for (int r = 0; r < TS; r += 2)
+            {
+                unsigned n0 = 0, n1 = 0;
+                T v0 = 0, v1 = 0;
+                if (r < rowlen)
+                {
+                    int p = o + (int)s * rowlen + r;
+                    v0 = a.Blockell_Val[p];
+                    n0 = nib_global(a.ell_compressedIdx, p);
+                }
+                if (r + 1 < rowlen)
+                {
+                    int p = o + (int)s * rowlen + r + 1;
+                    v1 = a.Blockell_Val[p];
+                    n1 = nib_global(a.ell_compressedIdx, p);
+                }
+                pv[s * 16 + r] = v0;
+                pv[s * 16 + r + 1] = v1;
+                ix[(s * 16 + r) >> 1] = (unsigned char)((n0 << 4) | n1);
+            }
+        }
+        break;
+    }
+    case TILESPMV_FMT_DENSE:
+    {
+        const int o = a.dns_offset[t];
+        for (int c = 0; c < TS; c++)
+            for (int r = 0; r < TS; r++)
+                pv[c * 16 + r] = (c < collen && r < rowlen) ? a.Blockdense_Val[o + c * rowlen + r] : (T)0;
+        break;
+    }
+    case TILESPMV_FMT_DENSEROW:
+    {
+        const int o = a.dnsrow_offset[t], ro = a.dnsrowptr[t];
+        const int ndr = a.dnsrowptr[t + 1] - ro;
+        w = (uint32_t)ndr;
+        for (int i = 0; i < ndr; i++)
+        {
+            aux |= 1u << ((unsigned)a.denserowid[ro + i] & 15u);
+            for (int c = 0; c < TS; c++)
+                pv[i * 16 + c] = c < collen ? a.Blockdenserow_Val[o + i * collen + c] : (T)0;
+        }
+        break;
+    }
+    case TILESPMV_FMT_DENSECOL:
+    {
+        const int o = a.dnscol_offset[t], co = a.dnscolptr[t];
+        const int ndc = a.dnscolptr[t + 1] - co;
+        w = (uint32_t)ndc;
+        unsigned long long ids = 0;
+        for (int k = 0; k < ndc; k++)
+        {
+            ids |= (unsigned long long)((unsigned)a.densecolid[co + k] & 15u) << (4 * k);
+            for (int r = 0; r < TS; r++)
+                pv[k * 16 + r] = r < rowlen ? a.Blockdensecol_Val[o + k * rowlen + r] : (T)0;
+        }
+        *reinterpret_cast<unsigned long long *>(pay + (size_t)ndc * 16 * sizeof(T)) = ids;
+        break;
+    }
+    default:
+        break;
+    }
+    uint2 d;
+    d.x = (uint32_t)tc;
+    d.y = (uint32_t)f | (w << 8) | (aux << 16);
+    *reinterpret_cast<uint2 *>(desc_out) = d;
+}
+
+template <class T>
+__global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long long nchunks)
+{
+    extern __shared__ int s_base[]; // per item: tile base, payload base, side base, side-count index
+    __shared__ ChunkHeader hdr;
+    const long long c = blockIdx.x;
+    if (c >= nchunks)
+        return;
+    const long long i0 = a.chunk_item0[c], i1 = a.chunk_item0[c + 1];
+    const int nitems = (int)(i1 - i0);
+    unsigned char *out = a.stream + a.chunk_off[c];
+    constexpr uint32_t vs = (uint32_t)sizeof(T);
+
+    if (threadIdx.x == 0)
+    {
+        uint32_t ntiles = 0, pay = 0, nside = 0, nsiderows = 0;
+        for (int k = 0; k < nitems; k++)
+        {
+            const PlanItem it = a.items[i0 + k];
+            const int nt = a.ncscan[it.t1] - a.ncscan[it.t0];
+            const uint32_t pb = (uint32_t)(a.pbscan[it.t1] - a.pbscan[it.t0]) - 8u * (uint32_t)nt;
+            const int ns = it.s1 - it.s0;
+            s_base[4 * k + 0] = (int)ntiles;
+            s_base[4 * k + 1] = (int)pay;
+            s_base[4 * k + 2] = (int)nside;
+            s_base[4 * k + 3] = (int)nsiderows;
+            uint2 rec;
+            rec.x = it.dest;
+            rec.y = (uint32_t)nt | ((uint32_t)it.rowlen << 16) | ((ns > 0 ? ROWF_HAS_SIDE : 0u) << 24);
+            *reinterpret_cast<uint2 *>(out + 32 + 8 * k) = rec;
+            ntiles += (uint32_t)nt;
+            pay += pb;
+            nside += (uint32_t)ns;
+            nsiderows += ns > 0 ? 1u : 0u;
+        }
+        hdr.nrows = (uint16_t)nitems;
+        hdr.ntiles = (uint16_t)ntiles;
+        hdr.nside = nside;
+        hdr.off_tiledesc = 32u + 8u * (uint32_t)nitems;
+        hdr.off_sidecnt = hdr.off_tiledesc + 8u * ntiles;
+        hdr.off_sidecol = hdr.off_sidecnt + 32u * nsiderows;
+        hdr.off_sideval = hdr.off_sidecol + pad8(4u * nside);
+        hdr.off_payload = hdr.off_sideval + pad8(vs * nside);
+        hdr.total_bytes = pad16(hdr.off_payload + pay);
+        *reinterpret_cast<ChunkHeader *>(out) = hdr;
+        if ((unsigned long long)hdr.total_bytes != a.chunk_off[c + 1] - a.chunk_off[c])
+            atomicExch(a.error_flag, 1);
+    }
+    __syncthreads();
+
+    for (int k = 0; k < nitems; k++)
+    {
+        const PlanItem it = a.items[i0 + k];
+        // tiles of this item, one thread per tile
+        for (int t = it.t0 + (int)threadIdx.x; t < it.t1; t += PACK_THREADS)
+        {
+            if (a.Format[t] == TILESPMV_FMT_COO)
+                continue;
+            const int li = a.ncscan[t] - a.ncscan[it.t0];
+            const uint32_t poff = (uint32_t)(a.pbscan[t] - a.pbscan[it.t0]) - 8u * (uint32_t)li;
+            pack_tile<T>(a, t, it.br, out + hdr.off_tiledesc + 8u * (uint32_t)(s_base[4 * k + 0] + li),
+                         out + hdr.off_payload + (uint32_t)s_base[4 * k + 1] + poff);
+        }
+        const int ns = it.s1 - it.s0;
+        if (ns > 0)
+        {
+            if (threadIdx.x < TS)
+            {
+                // overlap of [s0,s1) with the side-CSR range of local row r
+                const int r = threadIdx.x;
+                int cnt = 0;
+                if (r < it.rowlen)
+                {
+                    int lo = a.side_ptr[it.br * TS + r], hi = a.side_ptr[it.br * TS + r + 1];
+                    lo = lo > it.s0 ? lo : it.s0;
+                    hi = hi < it.s1 ? hi : it.s1;
+                    cnt = hi > lo ? hi - lo : 0;
+                }
+                reinterpret_cast<uint16_t *>(out + hdr.off_sidecnt)[16 * s_base[4 * k + 3] + r] = (uint16_t)cnt;
+            }
+            uint32_t *oc = reinterpret_cast<uint32_t *>(out + hdr.off_sidecol) + s_base[4 * k + 2];
+            T *ov = reinterpret_cast<T *>(out + hdr.off_sideval) + s_base[4 * k + 2];
+            for (int e = threadIdx.x; e < ns; e += PACK_THREADS)
+            {
+                oc[e] = (uint32_t)a.side_col[it.s0 + e];
+                ov[e] = a.side_val[it.s0 + e];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: chunking
+// ---------------------------------------------------------------------------------------------
+namespace
+{
+struct ChunkAcc
+{
+    uint32_t nrows = 0, ntiles = 0, nsiderows = 0, nside = 0, payload = 0;
+    bool empty() const { return nrows == 0; }
+    uint32_t bytes(uint32_t vs) const { return chunk_layout_bytes(nrows, ntiles, nsiderows, nside, payload, vs); }
+    uint32_t xbytes(uint32_t vs) const { return ntiles * 16u * vs + nside * vs; }
+};
+} // namespace
+
+template <class T>
+static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t s)
+{
+    const uint32_t vs = (uint32_t)sizeof(T);
+    const int T_ = dm->tilenum, tilem = dm->tilem, rowA = dm->rowA;
+    const uint32_t C = (uint32_t)P->chunk_bytes, X = (uint32_t)P->xstage_bytes;
+    ScanWorkspace ws;
+
+    if (dm->fmt_hist[TILESPMV_FMT_HYB] > 0)
+    {
+        set_error("plan: HYB tiles are not supported yet (the default selector never emits them, csr2tile.h:308-316)");
+        return TILESPMV_ERR_UNSUPPORTED;
+    }
+
+    // ---- 1. per-tile stream cost prefix sums ----
+    DevBuf pbscan, ncscan;
+    TSP_TRY(pbscan.alloc((size_t)(T_ + 1) * sizeof(long long), true, s));
+    TSP_TRY(ncscan.alloc((size_t)(T_ + 1) * sizeof(int), true, s));
+    if (T_)
+    {
+        TileCostIn tc{dm->Format.as<char>(), dm->tile_nnz.as<int>(), dm->tilewidth.as<char>(),
+                      dm->dnsrowptr.as<int>(), dm->dnscolptr.as<int>(), T_, vs};
+        TSP_TRY(exclusive_scan(tc, (size_t)T_ + 1, pbscan.as<long long>(), ws, s, nullptr));
+        TSP_TRY(exclusive_scan(NonCooIn{dm->Format.as<char>(), T_}, (size_t)T_ + 1, ncscan.as<int>(), ws, s, nullptr));
+    }
+    DevBuf d_row_pay, d_row_nt, d_row_s0;
+    TSP_TRY(d_row_pay.alloc((size_t)(tilem + 1) * sizeof(long long), true, s));
+    TSP_TRY(d_row_nt.alloc((size_t)(tilem + 1) * sizeof(int), true, s));
+    TSP_TRY(d_row_s0.alloc((size_t)(tilem + 1) * sizeof(int), true, s));
+    TSP_LAUNCH(row_summary_kernel, grid_for((size_t)tilem + 1, PL_THREADS), PL_THREADS, 0, s, tilem, rowA,
+               dm->tile_ptr.as<int>(), pbscan.as<long long>(), ncscan.as<int>(), dm->deferredcoo_ptr.as<int>(),
+               d_row_pay.as<long long>(), d_row_nt.as<int>(), d_row_s0.as<int>());
+    std::vector<long long> row_pay(tilem + 1);
+    std::vector<int> row_nt(tilem + 1), row_s0(tilem + 1), tile_ptr(tilem + 1);
+    TSP_CUDA(cudaMemcpyAsync(row_pay.data(), d_row_pay.p, (size_t)(tilem + 1) * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    TSP_CUDA(cudaMemcpyAsync(row_nt.data(), d_row_nt.p, (size_t)(tilem + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+    TSP_CUDA(cudaMemcpyAsync(row_s0.data(), d_row_s0.p, (size_t)(tilem + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+    TSP_CUDA(cudaMemcpyAsync(tile_ptr.data(), dm->tile_ptr.p, (size_t)(tilem + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+    TSP_CUDA(cudaStreamSynchronize(s));
+
+    // ---- 2. greedy byte-bounded chunking over block rows ----
+    std::vector<PlanItem> items;
+    std::vector<long long> chunk_item0;
+    std::vector<unsigned long long> chunk_off;
+    std::vector<int> split_tab; // 4 ints per split row
+    items.reserve((size_t)tilem + 16);
+    unsigned long long off = 0;
+    int64_t nslots = 0;
+    ChunkAcc acc;
+    auto close_chunk = [&]() {
+        if (acc.empty())
+            return;
+        off += acc.bytes(vs);
+        chunk_off.push_back(off);
+        chunk_item0.push_back((long long)items.size());
+        acc = ChunkAcc();
+    };
+    chunk_off.push_back(0);
+    chunk_item0.push_back(0);
+    std::vector<long long> h_pb;
+    std::vector<int> h_nc;
+    for (int b = 0; b < tilem; b++)
+    {
+        const int rowlen = b == tilem - 1 ? rowA - (tilem - 1) * TS : TS;
+        const int nt = row_nt[b];
+        const int ns = row_s0[b + 1] - row_s0[b];
+        const long long pay_ll = row_pay[b] - 8ll * nt;
+        ChunkAcc one;
+        one.nrows = 1;
+        one.ntiles = (uint32_t)nt;
+        one.nside = (uint32_t)ns;
+        one.nsiderows = ns > 0 ? 1 : 0;
+        const bool fits_alone = pay_ll < (long long)C && nt < 65536 &&
+                                (one.payload = (uint32_t)pay_ll, one.bytes(vs) <= C) && one.xbytes(vs) <= X;
+        if (fits_alone)
+        {
+            ChunkAcc trial = acc;
+            trial.nrows += 1;
+            trial.ntiles += one.ntiles;
+            trial.nside += one.nside;
+            trial.nsiderows += one.nsiderows;
+            trial.payload += one.payload;
+            if (trial.bytes(vs) > C || trial.xbytes(vs) > X || trial.nrows > 65535u)
+            {
+                close_chunk();
+                trial = one;
+            }
+            acc = trial;
+            items.push_back(PlanItem{b, tile_ptr[b], tile_ptr[b + 1], row_s0[b], row_s0[b + 1], (uint32_t)b, rowlen});
+            continue;
+        }
+        // ---- long block row: cut into pieces, each piece is its own chunk ----
+        close_chunk();
+        const int ta = tile_ptr[b], tb = tile_ptr[b + 1];
+        const int64_t slot0 = nslots;
+        if (nt > 0)
+        {
+            const size_t cntt = (size_t)(tb - ta) + 1;
+            h_pb.resize(cntt);
+            h_nc.resize(cntt);
+            TSP_CUDA(cudaMemcpyAsync(h_pb.data(), pbscan.as<long long>() + ta, cntt * sizeof(long long), cudaMemcpyDeviceToHost, s));
+            TSP_CUDA(cudaMemcpyAsync(h_nc.data(), ncscan.as<int>() + ta, cntt * sizeof(int), cudaMemcpyDeviceToHost, s));
+            TSP_CUDA(cudaStreamSynchronize(s));
+            int t = ta;
+            while (t < tb)
+            {
+                int te = t;
+                ChunkAcc piece;
+                piece.nrows = 1;
+                while (te < tb)
+                {
+                    const uint32_t is_tile = (uint32_t)(h_nc[te + 1 - ta] - h_nc[te - ta]);
+                    const uint32_t pb = (uint32_t)(h_pb[te + 1 - ta] - h_pb[te - ta]) - 8u * is_tile;
+                    ChunkAcc trial = piece;
+                    trial.ntiles += is_tile;
+                    trial.payload += pb;
+                    if (is_tile && piece.ntiles > 0 && (trial.bytes(vs) > C || trial.xbytes(vs) > X))
+                        break;
+                    piece = trial;
+                    te++;
+                }
+                if (piece.ntiles > 0)
+                {
+                    acc = piece;
+                    items.push_back(PlanItem{b, t, te, row_s0[b], row_s0[b], ROW_PARTIAL | (uint32_t)nslots, rowlen});
+                    nslots++;
+                    close_chunk();
+                }
+                t = te;
+            }
+        }
+        if (ns > 0)
+        {
+            const uint32_t fixed = 32u + 8u + 32u + 16u + 16u;
+            uint32_t max_side = (C - fixed) / (4u + vs);
+            if (max_side > X / vs)
+                max_side = X / vs;
+            for (int s0 = row_s0[b]; s0 < row_s0[b + 1]; s0 += (int)max_side)
+            {
+                const int s1 = std::min(s0 + (int)max_side, row_s0[b + 1]);
+                acc.nrows = 1;
+                acc.nside = (uint32_t)(s1 - s0);
+                acc.nsiderows = 1;
+                items.push_back(PlanItem{b, tb, tb, s0, s1, ROW_PARTIAL | (uint32_t)nslots, rowlen});
+                nslots++;
+                close_chunk();
+            }
+        }
+        if (nslots == slot0)
+        {
+            // cannot happen (a long row has tiles or side entries); keep y defined anyway
+            acc.nrows = 1;
+            items.push_back(PlanItem{b, ta, ta, row_s0[b], row_s0[b], (uint32_t)b, rowlen});
+            close_chunk();
+        }
+        else
+        {
+            split_tab.push_back(b);
+            split_tab.push_back((int)slot0);
+            split_tab.push_back((int)(nslots - slot0));
+            split_tab.push_back(rowlen);
+        }
+        if (nslots > 0x7ffffff0ll)
+        {
+            set_error("plan: too many partial-sum slots");
+            return TILESPMV_ERR_UNSUPPORTED;
+        }
+    }
+    close_chunk();
+    const long long nchunks = (long long)chunk_off.size() - 1;
+    P->nchunks = nchunks;
+    P->stream_bytes = (int64_t)off;
+    P->nsplit = (int64_t)split_tab.size() / 4;
+    P->nslots = nslots;
+
+    // ---- 3. upload tables, pack ----
+    DevBuf d_items, d_chunk_item0, d_err;
+    TSP_TRY(d_items.alloc(items.size() * sizeof(PlanItem), false));
+    TSP_TRY(d_chunk_item0.alloc(chunk_item0.size() * sizeof(long long), false));
+    TSP_TRY(P->chunk_off.alloc(chunk_off.size() * sizeof(unsigned long long), false));
+    TSP_TRY(P->stream.alloc((size_t)off + 16, true, s));
+    TSP_TRY(d_err.alloc(sizeof(int), true, s));
+    TSP_TRY(P->scratch.alloc((size_t)nslots * TS * vs, true, s));
+    TSP_TRY(P->split_tab.alloc(split_tab.size() * sizeof(int), false));
+    if (!items.empty())
+        TSP_CUDA(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(PlanItem), cudaMemcpyHostToDevice, s));
+    TSP_CUDA(cudaMemcpyAsync(d_chunk_item0.p, chunk_item0.data(), chunk_item0.size() * sizeof(long long), cudaMemcpyHostToDevice, s));
+    TSP_CUDA(cudaMemcpyAsync(P->chunk_off.p, chunk_off.data(), chunk_off.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+    if (!split_tab.empty())
+        TSP_CUDA(cudaMemcpyAsync(P->split_tab.p, split_tab.data(), split_tab.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+
+    if (nchunks > 0)
+    {
+        long long max_items = 0;
+        for (long long c = 0; c < nchunks; c++)
+            max_items = std::max(max_items, chunk_item0[c + 1] - chunk_item0[c]);
+        PackArgs<T> a;
+        a.items = d_items.as<PlanItem>();
+        a.chunk_item0 = d_chunk_item0.as<long long>();
+        a.chunk_off = P->chunk_off.as<unsigned long long>();
+        a.pbscan = pbscan.as<long long>();
+        a.ncscan = ncscan.as<int>();
+        a.stream = P->stream.as<unsigned char>();
+        a.error_flag = d_err.as<int>();
+        a.rowA = dm->rowA;
+        a.colA = dm->colA;
+        a.tilem = dm->tilem;
+        a.tilen = dm->tilen;
+        a.tile_columnidx = dm->tile_columnidx.as<int>();
+        a.tile_nnz = dm->tile_nnz.as<int>();
+        a.Format = dm->Format.as<char>();
+        a.tilewidth = dm->tilewidth.as<char>();
+        a.csr_offset = dm->csr_offset.as<int>();
+        a.csrptr_offset = dm->csrptr_offset.as<int>();
+        a.ell_offset = dm->ell_offset.as<int>();
+        a.dns_offset = dm->dns_offset.as<int>();
+        a.dnsrow_offset = dm->dnsrow_offset.as<int>();
+        a.dnscol_offset = dm->dnscol_offset.as<int>();
+        a.dnsrowptr = dm->dnsrowptr.as<int>();
+        a.dnscolptr = dm->dnscolptr.as<int>();
+        a.Blockcsr_Val = dm->Blockcsr_Val.as<T>();
+        a.Blockell_Val = dm->Blockell_Val.as<T>();
+        a.Blockdense_Val = dm->Blockdense_Val.as<T>();
+        a.Blockdenserow_Val = dm->Blockdenserow_Val.as<T>();
+        a.Blockdensecol_Val = dm->Blockdensecol_Val.as<T>();
+        a.Blockcsr_Ptr = dm->Blockcsr_Ptr.as<unsigned char>();
+        a.csr_compressedIdx = dm->csr_compressedIdx.as<unsigned char>();
+        a.ell_compressedIdx = dm->ell_compressedIdx.as<unsigned char>();
+        a.denserowid = dm->denserowid.as<char>();
+        a.densecolid = dm->densecolid.as<char>();
+        a.side_ptr = dm->deferredcoo_ptr.as<int>();
+        a.side_col = dm->deferredcoo_colidx.as<int>();
+        a.side_val = dm->deferredcoo_val.as<T>();
+        const size_t shm = (size_t)max_items * 4 * sizeof(int);
+        if (shm > 200 * 1024)
+        {
+            set_error("plan: too many block rows in one chunk");
+            return TILESPMV_ERR_UNSUPPORTED;
+        }
+        if (shm > 48 * 1024)
+            TSP_CUDA(cudaFuncSetAttribute(pack_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+        if (nchunks > 0x7fffffffll)
+        {
+            set_error("plan: too many chunks");
+            return TILESPMV_ERR_UNSUPPORTED;
+        }
+        TSP_LAUNCH((pack_kernel<T>), (unsigned)nchunks, PACK_THREADS, shm, s, a, nchunks);
+    }
+    int h_err = 0;
+    TSP_CUDA(cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    TSP_CUDA(cudaStreamSynchronize(s));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+    {
+        set_error("plan: pack kernel failed: %s", cudaGetErrorString(e));
+        return TILESPMV_ERR_CUDA;
+    }
+    if (h_err)
+    {
+        set_error("plan: internal error, chunk layout size mismatch between host and device");
+        return TILESPMV_ERR_CUDA;
+    }
+    return TILESPMV_OK;
+}
+
+int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tilespmv_plan *P, cudaStream_t s)
+{
+    P->precision = dm->precision;
+    P->rowA = dm->rowA;
+    P->colA = dm->colA;
+    P->tilem = dm->tilem;
+    P->nnz = dm->nnz;
+    const int vs = dm->precision;
+    P->chunk_bytes = opts && opts->chunk_bytes ? opts->chunk_bytes : 4096;
+    P->xstage_bytes = opts && opts->xstage_bytes ? opts->xstage_bytes : (vs == 8 ? 3072 : 2048);
+    P->ctas_per_sm = opts ? opts->ctas_per_sm : 0;
+    if (P->chunk_bytes < 2560 || P->chunk_bytes > 32768 || (P->chunk_bytes & 127) || P->xstage_bytes < 16 * vs ||
+        P->xstage_bytes > 32768 || (P->xstage_bytes & 127))
+    {
+        set_error("plan: chunk_bytes must be a multiple of 128 in [2560, 32768], xstage_bytes a multiple of 128 in [%d, 32768]",
+                  16 * vs);
+        return TILESPMV_ERR_INVALID;
+    }
+    TSP_TRY(spmv_configure(P));
+    if (vs == 8)
+        TSP_TRY(plan_build_t<double>(dm, P, s));
+    else
+        TSP_TRY(plan_build_t<float>(dm, P, s));
+
+    // roofline accounting, SURVEY.md 8(d): every quantity from the (bit-exact) Tile_matrix
+    const int64_t T_coo = dm->fmt_hist[TILESPMV_FMT_COO], T_csr = dm->fmt_hist[TILESPMV_FMT_CSR];
+    const int64_t nnz_ext = dm->coototal, nnz_tiled = dm->nnz - nnz_ext, T_tiled = (int64_t)dm->tilenum - T_coo;
+    const int64_t m = dm->rowA, n = dm->colA;
+    P->b_alg = (nnz_tiled * (2 * vs + 1)) / 2 + 5 * T_tiled + 16 * T_csr + 4 * ((int64_t)dm->tilem + 1) +
+               nnz_ext * (vs + 4) + (nnz_ext > 0 ? 4 * (m + 1) : 0) + (int64_t)vs * (n + m);
+    P->b_csr = dm->nnz * (vs + 4) + 4 * (m + 1) + (int64_t)vs * (n + m);
+    return TILESPMV_OK;
+}
+
+} // namespace tsp

@@ -1,0 +1,52 @@
+// plan.cuh -- tilespmv_plan: packed stream + chunk schedule + launch configuration.
+#pragma once
+#include "dmat.cuh"
+#include "stream.cuh"
+
+constexpr int TSP_MAX_PEERS = 8;
+
+struct tilespmv_plan
+{
+    int precision = TILESPMV_F64;
+    int rowA = 0, colA = 0, tilem = 0;
+    int64_t nnz = 0;
+
+    // packed stream
+    int chunk_bytes = 0, xstage_bytes = 0;
+    int64_t nchunks = 0;
+    int64_t stream_bytes = 0;
+    tsp::DevBuf stream;    // the packed bytes
+    tsp::DevBuf chunk_off; // uint64[nchunks+1], 16-byte aligned offsets into stream
+
+    // block rows that were cut across chunks: partial sums land in scratch and are combined by the
+    // fix-up kernel in a fixed order (deterministic, no atomics)
+    int64_t nsplit = 0, nslots = 0;
+    tsp::DevBuf scratch;   // T[nslots*16]
+    tsp::DevBuf split_tab; // int4 {block row, first slot, #slots, rowlen} per split row
+
+    // launch configuration of the persistent kernel
+    int grid = 0, block = 0, smem = 0, ctas_per_sm = 0, sm_count = 0;
+
+    // roofline accounting
+    int64_t b_alg = 0, b_csr = 0;
+
+    // fused all-gather epilogue
+    int npeers = 0;
+    void *peers[TSP_MAX_PEERS] = {nullptr};
+    int64_t row_offset = 0;
+
+    // device staging for the host-pointer entry point
+    tsp::DevBuf hx, hy;
+
+    int64_t device_bytes() const
+    {
+        return (int64_t)(stream.bytes + chunk_off.bytes + scratch.bytes + split_tab.bytes + hx.bytes + hy.bytes);
+    }
+};
+
+namespace tsp
+{
+int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tilespmv_plan *plan, cudaStream_t s);
+int plan_launch(tilespmv_plan *plan, const void *d_x, void *d_y, cudaStream_t s);
+int spmv_configure(tilespmv_plan *plan); // picks grid / smem, sets the kernel attributes
+} // namespace tsp
