@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- fp64 SpMV GFLOP/s (2*nnz/t) + achieved HBM GB/s for the TileSpMV hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+A "step" is one y = A*x through tilespmv_plan_spmv (device-resident inputs).  N=1 runs BASELINE
+config 2 (3-D 27-point Laplacian 160^3, fp64, ~109 M nnz); N>1 runs one such row block per GPU
+(weak scaling: a 160N x 160 x 160 grid cut into N slabs, x replicated, no data-path collective for
+a single SpMV) and additionally reports the repeated-SpMV loop with the per-iteration x all-gather.
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with CUDA events on the launching stream;
+`e2e` is the same metric through the C-ABI with HOST buffers (pinned H2D of x + D2H of y inside the
+timed region); `roofline` relates the SpMV kernel to the measured HBM copy bandwidth
+(MEASURED_PEAKS.json); `cpu_baseline` times the reference's own CPU path (oracle/_ref, else the
+oracle port) on a bounded sample on this box's host cores.
+
+--impl reference times only that CPU path (rank 0) on the same metric / config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "fp64 SpMV GFLOP/s (2*nnz/t)"
+UNIT = "GFLOP/s"
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+CPU_SAMPLE_GRID = 96       # 3-D 27-pt Laplacian 96^3: same tile mix as config 2, 1/4.6 of its rows
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(workload):
+    """dram__bytes_read+write per launch of tile_spmv_kernel from the committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.thread, self.idx = [], None, None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.idx)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (the only place bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(steps=3):
+    """Reference CPU path (tilespmv_cpu, tilespmv_cpu.h:3-285; serial => 1 core) on a bounded sample."""
+    from oracle import oracle_py as O
+    from tilespmv_b200 import generators as g
+    G = CPU_SAMPLE_GRID
+    m, n, rp, ci, v = g.lap3d27(G, val_mode=0)
+    ora = O.Oracle("f64")
+    t0 = time.time()
+    M = ora.tile_create(m, n, rp, ci, v)  # conversion by the O(nnz log nnz) port (untimed set-up)
+    t_conv = time.time() - t0
+    x = np.random.default_rng(1).uniform(-1, 1, n)
+    times = []
+    if O.ref_available("f64"):
+        ref, kind = O.Reference("f64"), "reference"
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)  # the reference prints an errcount line per call
+        try:
+            for _ in range(steps):
+                ms, _ = ref.time_tilespmv_cpu(M, m, n, rp, ci, v, x)
+                times.append(ms)
+        finally:
+            os.dup2(saved, 1)
+            os.close(devnull)
+            os.close(saved)
+    else:
+        kind = "port"
+        for _ in range(steps):
+            ms, _ = ora.time_tilespmv_cpu(M, m, n, x)
+            times.append(ms)
+    nnz = int(rp[m])
+    best = min(times)
+    return {"value": 2.0 * nnz / (best * 1e-3) / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"3-D 27-pt Laplacian {G}^3 fp64 ({nnz} nnz, same ELL(w=3)+COO tile mix as config 2), "
+                      f"tilespmv_cpu whole call, best of {steps}; Tile_matrix built by the oracle port in {t_conv:.1f}s "
+                      f"with {ora.threads()} threads (untimed)",
+            "ms_per_call": best, "all_ms": times, "host_threads_available": ora.threads()}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 20))
+    warm = min(args.warmup, 2)
+    cb = cpu_baseline(steps + warm)
+    times = cb["all_ms"][warm:]
+    mean_ms = float(np.mean(times))
+    nnz_sample = (3 * CPU_SAMPLE_GRID - 2) ** 3
+    value = 2.0 * nnz_sample / (mean_ms * 1e-3) / 1e9
+    cb = dict(cb, value=value)
+    cb.pop("all_ms", None)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+           "warmup": warm, "ms_per_step": mean_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+           "cpu_baseline": cb,
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, world):
+    G = args.grid
+    return {"workload": f"3-D 27-point Laplacian {G * world}x{G}x{G} fp64 (BASELINE config 2 per GPU: {G}^3 rows, "
+                        f"~{(3 * G - 2) ** 3 / 1e6:.0f} M nnz per GPU), row-block sharded",
+            "per_gpu_rows": G ** 3, "partition": f"{world} contiguous row blocks of tiles, x replicated",
+            "cache": "inputs larger than L2 (packed stream ~1.07 GB per GPU vs 126 MB L2); no flush"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from tilespmv_b200 import _capi, api, generators as g
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L = _capi.load()
+    G = args.grid
+    t0 = time.time()
+    m, n, rp, ci, v = g.lap3d27_slab(G * world, G, G, rank * G, (rank + 1) * G, val_mode=0)
+    nnz_local = int(rp[m])
+    t_gen = time.time() - t0
+    t0 = time.time()
+    dm = api.DeviceTileMatrix.from_csr(m, n, rp, ci, v)  # GPU csr2tile (incl. H2D of the CSR)
+    torch.cuda.synchronize()
+    t_conv = time.time() - t0
+    t0 = time.time()
+    plan = api.Plan(dm, chunk_bytes=args.chunk_bytes, xstage_bytes=args.xstage_bytes, ctas_per_sm=args.ctas_per_sm)
+    torch.cuda.synchronize()
+    t_plan = time.time() - t0
+    pi, di = plan.info(), dm.info()
+
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    x = (torch.rand(n, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1)
+    y = torch.empty(m, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # sanity: the kernel's y against torch's own CSR SpMV on the same device data
+    plan.spmv(x.data_ptr(), y.data_ptr(), stream)
+    A = torch.sparse_csr_tensor(torch.from_numpy(rp).cuda().long(), torch.from_numpy(ci).cuda().long(),
+                                torch.from_numpy(v).cuda(), size=(m, n))
+    y_chk = A @ x
+    scale = torch.sparse_csr_tensor(A.crow_indices(), A.col_indices(), A.values().abs(), size=(m, n)) @ x.abs()
+    ok = bool(((y - y_chk).abs() <= 1e-12 * scale.clamp_min(1e-300)).all())
+    del A, y_chk, scale
+    if not ok:
+        raise SystemExit("bench: SpMV result check failed")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank])
+    for _ in range(args.warmup):
+        plan.spmv(x.data_ptr(), y.data_ptr(), stream)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = L.tilespmv_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        plan.spmv(x.data_ptr(), y.data_ptr(), stream)
+    e1.record()
+    barrier()
+    launches = L.tilespmv_kernel_launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    nnz_total = nnz_local
+    if dist is not None:
+        t = torch.tensor([nnz_local], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        nnz_total = int(t.item())
+    value = 2.0 * nnz_total / (ms_step * 1e-3) / 1e9
+
+    # ---- end-to-end through the C-ABI with host buffers (pinned), H2D + SpMV + D2H per step ----
+    xh = torch.empty(n, dtype=torch.float64).pin_memory()
+    xh.copy_(x.cpu())
+    yh = torch.empty(m, dtype=torch.float64).pin_memory()
+    e2e_steps = max(3, min(args.steps, 30))
+    for _ in range(2):
+        _capi.check(L.tilespmv_plan_spmv_host(plan.handle, xh.data_ptr(), yh.data_ptr()))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        _capi.check(L.tilespmv_plan_spmv_host(plan.handle, xh.data_ptr(), yh.data_ptr()))
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = 2.0 * nnz_total / (e2e_ms * 1e-3) / 1e9
+    e2e_ok = bool(torch.equal(yh.cuda(), y))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- repeated SpMV with the per-iteration all-gather of x (multi-GPU only) ----
+    iterate = None
+    if dist is not None:
+        xs = [torch.zeros(n, dtype=torch.float64, device="cuda") for _ in range(2)]
+        xs[0].copy_(x)
+        it_steps = max(3, min(args.steps, 50))
+
+        def loop(k):
+            for i in range(k):
+                src, dst = xs[i & 1], xs[(i + 1) & 1]
+                plan.spmv(src.data_ptr(), y.data_ptr(), stream)
+                dist.all_gather_into_tensor(dst, y)
+        loop(2)
+        barrier()
+        e0.record()
+        loop(it_steps)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / it_steps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        it_ms = float(t.item())
+        iterate = {"value": 2.0 * nnz_total / (it_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_iteration": it_ms,
+                   "collective": "NCCL all_gather_into_tensor of y slices into the next x",
+                   "allgather_bytes_per_gpu_in": (world - 1) * m * 8}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        b_alg = pi.algorithmic_bytes
+        achieved = b_alg / (ms_step * 1e-3) / 1e9
+        cb = cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
+        if cb:
+            cb.pop("all_ms", None)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": m * 8,
+                    "ms_per_step": e2e_ms, "api": "tilespmv_plan_spmv_host (pinned host x -> host y)", "matches_device_y": e2e_ok},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": recorded_traffic("c2_lap3d27_160"), "peak_source": peak_src,
+                         "kernel": "tsp::tile_spmv_kernel<double>", "algorithmic_bytes_per_launch": b_alg,
+                         "stream_bytes_per_launch": pi.stream_bytes, "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "timing": "CUDA events on the launching stream over the timed steps / steps"},
+            "cpu_baseline": cb,
+            "extra": {"nnz_total": nnz_total, "rows_per_gpu": m, "tilenum": di.tilenum, "nnz_side": di.nnz_side,
+                      "tiles_by_format": list(di.tiles_by_format), "chunks": pi.nchunks, "split_rows": pi.split_rows,
+                      "grid": pi.grid, "block": pi.block, "smem_bytes": pi.smem_bytes, "chunk_bytes": pi.chunk_bytes,
+                      "xstage_bytes": pi.xstage_bytes, "launches_per_spmv": pi.launches_per_spmv,
+                      "csr_bytes": pi.csr_bytes, "gen_s": t_gen, "convert_s_incl_h2d": t_conv, "plan_s": t_plan,
+                      "result_check_vs_torch_csr": ok, "library": os.path.basename(_capi.lib_path())},
+        }
+        if iterate:
+            out["iterate"] = iterate
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)   # BENCH_REPEAT of the reference (common.h:16-18)
+    ap.add_argument("--warmup", type=int, default=200)   # WARMUP_NUM (common.h:20-22)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=160)
+    ap.add_argument("--chunk-bytes", type=int, default=0)
+    ap.add_argument("--xstage-bytes", type=int, default=0)
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -125,6 +125,54 @@ int64_t tsgen_lap3d27(int G, int val_mode, int *rowptr, int *colidx, double *val
     return nnz;
 }
 
+/* ---- slab [i0,i1) of the 27-point Laplacian on an nx x ny x nz grid (row = (i*ny+j)*nz+k):
+        local rows, GLOBAL columns -- the row block one GPU owns in the multi-GPU runs ---- */
+int64_t tsgen_lap3d27_slab(int nx, int ny, int nz, int i0, int i1, int val_mode, int *rowptr, int *colidx,
+                           double *val)
+{
+    const int64_t plane = (int64_t)ny * nz;
+    const int64_t m = (int64_t)(i1 - i0) * plane;
+    int64_t nnz = 0;
+    for (int i = i0; i < i1; i++)
+    {
+        int ci = 1 + (i > 0) + (i < nx - 1);
+        nnz += (int64_t)ci * (3 * (int64_t)ny - 2) * (3 * (int64_t)nz - 2);
+    }
+    if (!rowptr)
+        return nnz;
+#pragma omp parallel for schedule(static, 4096)
+    for (int64_t r = 0; r < m; r++)
+    {
+        int k = (int)(r % nz), j = (int)((r / nz) % ny), i = i0 + (int)(r / plane);
+        rowptr[r] = (1 + (i > 0) + (i < nx - 1)) * (1 + (j > 0) + (j < ny - 1)) * (1 + (k > 0) + (k < nz - 1));
+    }
+    rowptr[m] = 0;
+    prefix_from_counts(m, rowptr);
+#pragma omp parallel for schedule(static, 4096)
+    for (int64_t r = 0; r < m; r++)
+    {
+        int k = (int)(r % nz), j = (int)((r / nz) % ny), i = i0 + (int)(r / plane);
+        int p = rowptr[r];
+        for (int di = -1; di <= 1; di++)
+        {
+            if (i + di < 0 || i + di >= nx) continue;
+            for (int dj = -1; dj <= 1; dj++)
+            {
+                if (j + dj < 0 || j + dj >= ny) continue;
+                for (int dk = -1; dk <= 1; dk++)
+                {
+                    if (k + dk < 0 || k + dk >= nz) continue;
+                    colidx[p] = (int)(((int64_t)(i + di) * ny + (j + dj)) * nz + (k + dk));
+                    val[p++] = (di == 0 && dj == 0 && dk == 0) ? 26.0 : -1.0;
+                }
+            }
+        }
+    }
+    if (val_mode == 1)
+        fill_values(m, rowptr, val, 1, 0);
+    return nnz;
+}
+
 /* ---- banded FEM-like: diagonal + `per_row` distinct offsets in [-hb,hb]\{0}, clipped (config 3) ---- */
 static int banded_row(int64_t N, int64_t i, int hb, int per_row, uint64_t seed, int *cols)
 {

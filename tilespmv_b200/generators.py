@@ -18,7 +18,7 @@ def _L():
     if _lib is None:
         _lib = C.CDLL(build.build_gen())
         for name in ("tsgen_lap2d", "tsgen_lap3d27", "tsgen_banded", "tsgen_band_contig",
-                     "tsgen_uniform_rows", "tsgen_rmat", "tsgen_seven_formats"):
+                     "tsgen_uniform_rows", "tsgen_rmat", "tsgen_seven_formats", "tsgen_lap3d27_slab"):
             getattr(_lib, name).restype = C.c_int64
     return _lib
 
@@ -54,6 +54,18 @@ def lap3d27(G, val_mode=0):
     rp, ci, v = _alloc(G ** 3, nnz)
     f(C.c_int(G), C.c_int(val_mode), *_ptrs(rp, ci, v))
     return G ** 3, G ** 3, rp, ci, v
+
+
+def lap3d27_slab(nx, ny, nz, i0, i1, val_mode=0):
+    """Planes [i0,i1) of the 27-point Laplacian on an nx x ny x nz grid: local rows, global columns
+    (the row block one GPU owns in multi-GPU runs).  Returns (m_local, n_global, rowptr, colidx, val)."""
+    f = _L().tsgen_lap3d27_slab
+    a = (C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(i0), C.c_int(i1), C.c_int(val_mode))
+    nnz = f(*a, *_NULLS)
+    m = (i1 - i0) * ny * nz
+    rp, ci, v = _alloc(m, nnz)
+    f(*a, *_ptrs(rp, ci, v))
+    return m, nx * ny * nz, rp, ci, v
 
 
 def banded(N, hb=64, per_row=36, seed=3, val_mode=0):
