@@ -17,9 +17,16 @@ constexpr int PL_THREADS = 256;
 constexpr int PACK_THREADS = 128;
 
 // ---------------------------------------------------------------------------------------------
-// 1. per-tile costs
+// 1. per-tile costs (prefix sums over tiles in Tile_matrix order)
 // ---------------------------------------------------------------------------------------------
-struct TileCostIn // 8 B descriptor + payload for tiles that live in the stream, 0 for COO tiles
+enum TileCostKind
+{
+    TC_STREAM_TILES, // 1 for every tile that lives in the stream (everything but COO)
+    TC_OTHER_TILES,  // 1 for CSR / Dense / DenseRow / DenseCol
+    TC_SLOTROWS,     // ELL / HYB width
+    TC_OTHER_BYTES   // payload bytes of the non-ELL tiles
+};
+struct TileCostIn
 {
     const char *fmt;
     const int *tile_nnz;
@@ -27,32 +34,44 @@ struct TileCostIn // 8 B descriptor + payload for tiles that live in the stream,
     const int *dnsrowptr, *dnscolptr;
     int T;
     uint32_t vs;
+    int kind;
     __device__ __forceinline__ int operator()(size_t i) const
     {
         if (i >= (size_t)T)
             return 0;
         const int f = fmt[i];
-        if (f == TILESPMV_FMT_COO)
-            return 0;
-        const int nd = f == TILESPMV_FMT_DENSEROW ? dnsrowptr[i + 1] - dnsrowptr[i]
-                                                  : (f == TILESPMV_FMT_DENSECOL ? dnscolptr[i + 1] - dnscolptr[i] : 0);
-        return 8 + (int)tile_payload_bytes(f, tile_nnz[i + 1] - tile_nnz[i], (int)width[i], nd, vs);
-    }
-};
-struct NonCooIn
-{
-    const char *fmt;
-    int T;
-    __device__ __forceinline__ int operator()(size_t i) const
-    {
-        return i < (size_t)T && fmt[i] != TILESPMV_FMT_COO ? 1 : 0;
+        switch (kind)
+        {
+        case TC_STREAM_TILES:
+            return f != TILESPMV_FMT_COO ? 1 : 0;
+        case TC_OTHER_TILES:
+            return fmt_is_other(f) ? 1 : 0;
+        case TC_SLOTROWS:
+            return fmt_is_ell(f) ? (int)(unsigned char)width[i] : 0;
+        default:
+        {
+            if (!fmt_is_other(f))
+                return 0;
+            const int nd = f == TILESPMV_FMT_DENSEROW ? dnsrowptr[i + 1] - dnsrowptr[i]
+                                                      : (f == TILESPMV_FMT_DENSECOL ? dnscolptr[i + 1] - dnscolptr[i] : 0);
+            return (int)other_payload_bytes(f, tile_nnz[i + 1] - tile_nnz[i], nd, vs);
+        }
+        }
     }
 };
 
+struct TileScans // all T+1 entries
+{
+    const int *nc;        // stream tiles
+    const int *oc;        // other tiles
+    const int *ws;        // slot-rows
+    const long long *ob;  // other payload bytes
+};
+
 __global__ void __launch_bounds__(PL_THREADS)
-    row_summary_kernel(int tilem, int rowA, const int *__restrict__ tile_ptr, const long long *__restrict__ pbscan,
-                       const int *__restrict__ ncscan, const int *__restrict__ side_ptr,
-                       long long *__restrict__ row_pay, int *__restrict__ row_nt, int *__restrict__ row_s0)
+    row_summary_kernel(int tilem, int rowA, const int *__restrict__ tile_ptr, TileScans sc,
+                       const int *__restrict__ side_ptr, int *__restrict__ row_nt, int *__restrict__ row_no,
+                       int *__restrict__ row_nsr, long long *__restrict__ row_ob, int *__restrict__ row_s0)
 {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b > tilem)
@@ -62,8 +81,10 @@ __global__ void __launch_bounds__(PL_THREADS)
     if (b < tilem)
     {
         int t0 = tile_ptr[b], t1 = tile_ptr[b + 1];
-        row_pay[b] = pbscan[t1] - pbscan[t0]; // includes 8 B of descriptor per stream tile
-        row_nt[b] = ncscan[t1] - ncscan[t0];
+        row_nt[b] = sc.nc[t1] - sc.nc[t0];
+        row_no[b] = sc.oc[t1] - sc.oc[t0];
+        row_nsr[b] = sc.ws[t1] - sc.ws[t0];
+        row_ob[b] = sc.ob[t1] - sc.ob[t0];
     }
 }
 
@@ -77,8 +98,7 @@ struct PackArgs
     const PlanItem *items;
     const long long *chunk_item0; // [nchunks+1]
     const unsigned long long *chunk_off;
-    const long long *pbscan;
-    const int *ncscan;
+    TileScans sc;
     unsigned char *stream;
     int *error_flag;
     // Tile_matrix (device)
@@ -100,9 +120,44 @@ __device__ __forceinline__ unsigned nib_global(const unsigned char *packed, int 
     return (pos & 1) ? (b & 15u) : (b >> 4);
 }
 
-// writes descriptor + payload of tile t; runs in ONE thread (payloads are <= 2 KB)
+// ELL tile -> w slot-rows of the row's ELL group (runs in one thread)
 template <class T>
-__device__ void pack_tile(const PackArgs<T> &a, int t, int br, unsigned char *desc_out, unsigned char *pay)
+__device__ void pack_ell_tile(const PackArgs<T> &a, int t, int br, unsigned xsel, T *vals, unsigned char *idx,
+                              unsigned char *xs)
+{
+    const int rowlen = br == a.tilem - 1 ? a.rowA - (a.tilem - 1) * TS : TS;
+    const int o = a.ell_offset[t];
+    const int w = (int)(unsigned char)a.tilewidth[t];
+    for (int s = 0; s < w; s++)
+    {
+        xs[s] = (unsigned char)xsel;
+        for (int r = 0; r < TS; r += 2)
+        {
+            unsigned n0 = 0, n1 = 0;
+            T v0 = 0, v1 = 0;
+            if (r < rowlen)
+            {
+                int p = o + s * rowlen + r;
+                v0 = a.Blockell_Val[p];
+                n0 = nib_global(a.ell_compressedIdx, p);
+            }
+            if (r + 1 < rowlen)
+            {
+                int p = o + s * rowlen + r + 1;
+                v1 = a.Blockell_Val[p];
+                n1 = nib_global(a.ell_compressedIdx, p);
+            }
+            vals[s * 16 + r] = v0;
+            vals[s * 16 + r + 1] = v1;
+            idx[(s * 16 + r) >> 1] = (unsigned char)((n0 << 4) | n1);
+        }
+    }
+}
+
+// non-ELL tile: descriptor + payload (runs in one thread; payloads are <= 2 KB)
+template <class T>
+__device__ void pack_other_tile(const PackArgs<T> &a, int t, int br, unsigned xsel, unsigned char *desc_out,
+                                unsigned char *pay)
 {
     const int f = a.Format[t];
     const int tc = a.tile_columnidx[t];
@@ -129,36 +184,6 @@ __device__ void pack_tile(const PackArgs<T> &a, int t, int br, unsigned char *de
             ix[k >> 1] = (unsigned char)((hi << 4) | lo);
         }
         aux = (uint32_t)nnz;
-        break;
-    }
-    case TILESPMV_FMT_ELL:
-    {
-        const int o = a.ell_offset[t];
-        w = (uint32_t)(unsigned char)a.tilewidth[t];
-        unsigned char *ix = pay + w * 16u * (uint32_t)sizeof(T);
-        for (uint32_t s = 0; s < w; s++)
-        {
-            for (int r = 0; r < TS; r += 2)
-            {
-                unsigned n0 = 0, n1 = 0;
-                T v0 = 0, v1 = 0;
-                if (r < rowlen)
-                {
-                    int p = o + (int)s * rowlen + r;
-                    v0 = a.Blockell_Val[p];
-                    n0 = nib_global(a.ell_compressedIdx, p);
-                }
-                if (r + 1 < rowlen)
-                {
-                    int p = o + (int)s * rowlen + r + 1;
-                    v1 = a.Blockell_Val[p];
-                    n1 = nib_global(a.ell_compressedIdx, p);
-                }
-                pv[s * 16 + r] = v0;
-                pv[s * 16 + r + 1] = v1;
-                ix[(s * 16 + r) >> 1] = (unsigned char)((n0 << 4) | n1);
-            }
-        }
         break;
     }
     case TILESPMV_FMT_DENSE:
@@ -201,15 +226,17 @@ __device__ void pack_tile(const PackArgs<T> &a, int t, int br, unsigned char *de
         break;
     }
     uint2 d;
-    d.x = (uint32_t)tc;
-    d.y = (uint32_t)f | (w << 8) | (aux << 16);
+    d.x = (uint32_t)f | (xsel << 8) | (w << 16);
+    d.y = aux;
     *reinterpret_cast<uint2 *>(desc_out) = d;
 }
+
+constexpr int PACK_ITEM_INTS = 6; // per item: tile base, other base, payload base, side base, sidehdr idx, nsr
 
 template <class T>
 __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long long nchunks)
 {
-    extern __shared__ int s_base[]; // per item: tile base, payload base, side base, side-count index
+    extern __shared__ int s_base[];
     __shared__ ChunkHeader hdr;
     const long long c = blockIdx.x;
     if (c >= nchunks)
@@ -221,73 +248,102 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long 
 
     if (threadIdx.x == 0)
     {
-        uint32_t ntiles = 0, pay = 0, nside = 0, nsiderows = 0;
+        uint32_t ntiles = 0, nother = 0, pay = 0, nside = 0, nsiderows = 0;
         for (int k = 0; k < nitems; k++)
         {
             const PlanItem it = a.items[i0 + k];
-            const int nt = a.ncscan[it.t1] - a.ncscan[it.t0];
-            const uint32_t pb = (uint32_t)(a.pbscan[it.t1] - a.pbscan[it.t0]) - 8u * (uint32_t)nt;
+            const int nt = a.sc.nc[it.t1] - a.sc.nc[it.t0];
+            const int no = a.sc.oc[it.t1] - a.sc.oc[it.t0];
+            const int nsr = a.sc.ws[it.t1] - a.sc.ws[it.t0];
+            const uint32_t ob = (uint32_t)(a.sc.ob[it.t1] - a.sc.ob[it.t0]);
             const int ns = it.s1 - it.s0;
-            s_base[4 * k + 0] = (int)ntiles;
-            s_base[4 * k + 1] = (int)pay;
-            s_base[4 * k + 2] = (int)nside;
-            s_base[4 * k + 3] = (int)nsiderows;
-            uint2 rec;
-            rec.x = it.dest;
-            rec.y = (uint32_t)nt | ((uint32_t)it.rowlen << 16) | ((ns > 0 ? ROWF_HAS_SIDE : 0u) << 24);
-            *reinterpret_cast<uint2 *>(out + 32 + 8 * k) = rec;
+            int *sb = s_base + PACK_ITEM_INTS * k;
+            sb[0] = (int)ntiles;
+            sb[1] = (int)nother;
+            sb[2] = (int)pay;
+            sb[3] = (int)nside;
+            sb[4] = (int)nsiderows;
+            sb[5] = nsr;
+            RowRec rec;
+            rec.dest = it.dest;
+            rec.nsr = (uint16_t)nsr;
+            rec.nother = (uint16_t)no;
+            rec.rowlen = (uint8_t)it.rowlen;
+            rec.flags = (uint8_t)(ns > 0 ? ROWF_HAS_SIDE : 0u);
+            rec.pad0 = 0;
+            rec.pad1 = 0;
+            *reinterpret_cast<RowRec *>(out + CHUNK_OFF_ROWS + 16 * k) = rec;
             ntiles += (uint32_t)nt;
-            pay += pb;
+            nother += (uint32_t)no;
+            pay += ell_group_bytes((uint32_t)nsr, vs) + ob;
             nside += (uint32_t)ns;
             nsiderows += ns > 0 ? 1u : 0u;
         }
         hdr.nrows = (uint16_t)nitems;
         hdr.ntiles = (uint16_t)ntiles;
         hdr.nside = nside;
-        hdr.off_tiledesc = 32u + 8u * (uint32_t)nitems;
-        hdr.off_sidecnt = hdr.off_tiledesc + 8u * ntiles;
-        hdr.off_sidecol = hdr.off_sidecnt + 32u * nsiderows;
+        hdr.nother = nother;
+        hdr.off_odesc = CHUNK_OFF_ROWS + 16u * (uint32_t)nitems + pad8(4u * ntiles);
+        hdr.off_sidehdr = hdr.off_odesc + 8u * nother;
+        hdr.off_sidecol = hdr.off_sidehdr + SIDEHDR_BYTES * nsiderows;
         hdr.off_sideval = hdr.off_sidecol + pad8(4u * nside);
-        hdr.off_payload = hdr.off_sideval + pad8(vs * nside);
-        hdr.total_bytes = pad16(hdr.off_payload + pay);
+        hdr.off_payload = pad16(hdr.off_sideval + pad8(vs * nside));
         *reinterpret_cast<ChunkHeader *>(out) = hdr;
-        if ((unsigned long long)hdr.total_bytes != a.chunk_off[c + 1] - a.chunk_off[c])
+        if ((unsigned long long)(hdr.off_payload + pay) != a.chunk_off[c + 1] - a.chunk_off[c])
             atomicExch(a.error_flag, 1);
     }
     __syncthreads();
+    uint32_t *tilecol = reinterpret_cast<uint32_t *>(out + CHUNK_OFF_ROWS + 16 * nitems);
 
     for (int k = 0; k < nitems; k++)
     {
         const PlanItem it = a.items[i0 + k];
+        const int *sb = s_base + PACK_ITEM_INTS * k;
+        const uint32_t nsr = (uint32_t)sb[5];
+        unsigned char *rowpay = out + hdr.off_payload + (uint32_t)sb[2];
+        T *ell_vals = reinterpret_cast<T *>(rowpay);
+        unsigned char *ell_idx = rowpay + nsr * 16u * vs;
+        unsigned char *ell_xsel = ell_idx + nsr * 8u;
+        unsigned char *other_pay = rowpay + ell_group_bytes(nsr, vs);
         // tiles of this item, one thread per tile
         for (int t = it.t0 + (int)threadIdx.x; t < it.t1; t += PACK_THREADS)
         {
-            if (a.Format[t] == TILESPMV_FMT_COO)
+            const int f = a.Format[t];
+            if (f == TILESPMV_FMT_COO)
                 continue;
-            const int li = a.ncscan[t] - a.ncscan[it.t0];
-            const uint32_t poff = (uint32_t)(a.pbscan[t] - a.pbscan[it.t0]) - 8u * (uint32_t)li;
-            pack_tile<T>(a, t, it.br, out + hdr.off_tiledesc + 8u * (uint32_t)(s_base[4 * k + 0] + li),
-                         out + hdr.off_payload + (uint32_t)s_base[4 * k + 1] + poff);
+            const unsigned xsel = (unsigned)(sb[0] + (a.sc.nc[t] - a.sc.nc[it.t0])); // x segment in the chunk
+            tilecol[xsel] = (uint32_t)a.tile_columnidx[t];
+            if (fmt_is_ell(f))
+            {
+                const uint32_t so = (uint32_t)(a.sc.ws[t] - a.sc.ws[it.t0]);
+                pack_ell_tile<T>(a, t, it.br, xsel, ell_vals + so * 16u, ell_idx + so * 8u, ell_xsel + so);
+            }
+            else
+            {
+                const uint32_t oi = (uint32_t)(sb[1] + (a.sc.oc[t] - a.sc.oc[it.t0]));
+                const uint32_t po = (uint32_t)(a.sc.ob[t] - a.sc.ob[it.t0]);
+                pack_other_tile<T>(a, t, it.br, xsel, out + hdr.off_odesc + 8u * oi, other_pay + po);
+            }
         }
         const int ns = it.s1 - it.s0;
         if (ns > 0)
         {
-            if (threadIdx.x < TS)
+            if (threadIdx.x <= TS)
             {
-                // overlap of [s0,s1) with the side-CSR range of local row r
+                // exclusive starts of every local row inside [s0,s1); entry 16 = ns
                 const int r = threadIdx.x;
-                int cnt = 0;
+                int st = ns;
                 if (r < it.rowlen)
                 {
-                    int lo = a.side_ptr[it.br * TS + r], hi = a.side_ptr[it.br * TS + r + 1];
+                    int lo = a.side_ptr[it.br * TS + r];
                     lo = lo > it.s0 ? lo : it.s0;
-                    hi = hi < it.s1 ? hi : it.s1;
-                    cnt = hi > lo ? hi - lo : 0;
+                    lo = lo < it.s1 ? lo : it.s1;
+                    st = lo - it.s0;
                 }
-                reinterpret_cast<uint16_t *>(out + hdr.off_sidecnt)[16 * s_base[4 * k + 3] + r] = (uint16_t)cnt;
+                reinterpret_cast<uint16_t *>(out + hdr.off_sidehdr + SIDEHDR_BYTES * (uint32_t)sb[4])[r] = (uint16_t)st;
             }
-            uint32_t *oc = reinterpret_cast<uint32_t *>(out + hdr.off_sidecol) + s_base[4 * k + 2];
-            T *ov = reinterpret_cast<T *>(out + hdr.off_sideval) + s_base[4 * k + 2];
+            uint32_t *oc = reinterpret_cast<uint32_t *>(out + hdr.off_sidecol) + sb[3];
+            T *ov = reinterpret_cast<T *>(out + hdr.off_sideval) + sb[3];
             for (int e = threadIdx.x; e < ns; e += PACK_THREADS)
             {
                 oc[e] = (uint32_t)a.side_col[it.s0 + e];
@@ -304,10 +360,19 @@ namespace
 {
 struct ChunkAcc
 {
-    uint32_t nrows = 0, ntiles = 0, nsiderows = 0, nside = 0, payload = 0;
+    uint32_t nrows = 0, ntiles = 0, nother = 0, nsiderows = 0, nside = 0, payload = 0;
     bool empty() const { return nrows == 0; }
-    uint32_t bytes(uint32_t vs) const { return chunk_layout_bytes(nrows, ntiles, nsiderows, nside, payload, vs); }
+    uint32_t bytes(uint32_t vs) const { return chunk_layout_bytes(nrows, ntiles, nother, nsiderows, nside, payload, vs); }
     uint32_t xbytes(uint32_t vs) const { return ntiles * 16u * vs + nside * vs; }
+    void add(const ChunkAcc &o)
+    {
+        nrows += o.nrows;
+        ntiles += o.ntiles;
+        nother += o.nother;
+        nsiderows += o.nsiderows;
+        nside += o.nside;
+        payload += o.payload;
+    }
 };
 } // namespace
 
@@ -325,30 +390,43 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
         return TILESPMV_ERR_UNSUPPORTED;
     }
 
-    // ---- 1. per-tile stream cost prefix sums ----
-    DevBuf pbscan, ncscan;
-    TSP_TRY(pbscan.alloc((size_t)(T_ + 1) * sizeof(long long), true, s));
-    TSP_TRY(ncscan.alloc((size_t)(T_ + 1) * sizeof(int), true, s));
+    // ---- 1. per-tile prefix sums ----
+    DevBuf d_nc, d_oc, d_ws, d_ob;
+    TSP_TRY(d_nc.alloc((size_t)(T_ + 1) * sizeof(int), true, s));
+    TSP_TRY(d_oc.alloc((size_t)(T_ + 1) * sizeof(int), true, s));
+    TSP_TRY(d_ws.alloc((size_t)(T_ + 1) * sizeof(int), true, s));
+    TSP_TRY(d_ob.alloc((size_t)(T_ + 1) * sizeof(long long), true, s));
     if (T_)
     {
         TileCostIn tc{dm->Format.as<char>(), dm->tile_nnz.as<int>(), dm->tilewidth.as<char>(),
-                      dm->dnsrowptr.as<int>(), dm->dnscolptr.as<int>(), T_, vs};
-        TSP_TRY(exclusive_scan(tc, (size_t)T_ + 1, pbscan.as<long long>(), ws, s, nullptr));
-        TSP_TRY(exclusive_scan(NonCooIn{dm->Format.as<char>(), T_}, (size_t)T_ + 1, ncscan.as<int>(), ws, s, nullptr));
+                      dm->dnsrowptr.as<int>(), dm->dnscolptr.as<int>(), T_, vs, TC_STREAM_TILES};
+        TSP_TRY(exclusive_scan(tc, (size_t)T_ + 1, d_nc.as<int>(), ws, s, nullptr));
+        tc.kind = TC_OTHER_TILES;
+        TSP_TRY(exclusive_scan(tc, (size_t)T_ + 1, d_oc.as<int>(), ws, s, nullptr));
+        tc.kind = TC_SLOTROWS;
+        TSP_TRY(exclusive_scan(tc, (size_t)T_ + 1, d_ws.as<int>(), ws, s, nullptr));
+        tc.kind = TC_OTHER_BYTES;
+        TSP_TRY(exclusive_scan(tc, (size_t)T_ + 1, d_ob.as<long long>(), ws, s, nullptr));
     }
-    DevBuf d_row_pay, d_row_nt, d_row_s0;
-    TSP_TRY(d_row_pay.alloc((size_t)(tilem + 1) * sizeof(long long), true, s));
-    TSP_TRY(d_row_nt.alloc((size_t)(tilem + 1) * sizeof(int), true, s));
-    TSP_TRY(d_row_s0.alloc((size_t)(tilem + 1) * sizeof(int), true, s));
-    TSP_LAUNCH(row_summary_kernel, grid_for((size_t)tilem + 1, PL_THREADS), PL_THREADS, 0, s, tilem, rowA,
-               dm->tile_ptr.as<int>(), pbscan.as<long long>(), ncscan.as<int>(), dm->deferredcoo_ptr.as<int>(),
-               d_row_pay.as<long long>(), d_row_nt.as<int>(), d_row_s0.as<int>());
-    std::vector<long long> row_pay(tilem + 1);
-    std::vector<int> row_nt(tilem + 1), row_s0(tilem + 1), tile_ptr(tilem + 1);
-    TSP_CUDA(cudaMemcpyAsync(row_pay.data(), d_row_pay.p, (size_t)(tilem + 1) * sizeof(long long), cudaMemcpyDeviceToHost, s));
-    TSP_CUDA(cudaMemcpyAsync(row_nt.data(), d_row_nt.p, (size_t)(tilem + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
-    TSP_CUDA(cudaMemcpyAsync(row_s0.data(), d_row_s0.p, (size_t)(tilem + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
-    TSP_CUDA(cudaMemcpyAsync(tile_ptr.data(), dm->tile_ptr.p, (size_t)(tilem + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+    TileScans sc{d_nc.as<int>(), d_oc.as<int>(), d_ws.as<int>(), d_ob.as<long long>()};
+    DevBuf d_row_nt, d_row_no, d_row_nsr, d_row_ob, d_row_s0;
+    const size_t nb1 = (size_t)tilem + 1;
+    TSP_TRY(d_row_nt.alloc(nb1 * sizeof(int), true, s));
+    TSP_TRY(d_row_no.alloc(nb1 * sizeof(int), true, s));
+    TSP_TRY(d_row_nsr.alloc(nb1 * sizeof(int), true, s));
+    TSP_TRY(d_row_ob.alloc(nb1 * sizeof(long long), true, s));
+    TSP_TRY(d_row_s0.alloc(nb1 * sizeof(int), true, s));
+    TSP_LAUNCH(row_summary_kernel, grid_for(nb1, PL_THREADS), PL_THREADS, 0, s, tilem, rowA, dm->tile_ptr.as<int>(), sc,
+               dm->deferredcoo_ptr.as<int>(), d_row_nt.as<int>(), d_row_no.as<int>(), d_row_nsr.as<int>(),
+               d_row_ob.as<long long>(), d_row_s0.as<int>());
+    std::vector<long long> row_ob(nb1);
+    std::vector<int> row_nt(nb1), row_no(nb1), row_nsr(nb1), row_s0(nb1), tile_ptr(nb1);
+    TSP_CUDA(cudaMemcpyAsync(row_ob.data(), d_row_ob.p, nb1 * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    TSP_CUDA(cudaMemcpyAsync(row_nt.data(), d_row_nt.p, nb1 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    TSP_CUDA(cudaMemcpyAsync(row_no.data(), d_row_no.p, nb1 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    TSP_CUDA(cudaMemcpyAsync(row_nsr.data(), d_row_nsr.p, nb1 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    TSP_CUDA(cudaMemcpyAsync(row_s0.data(), d_row_s0.p, nb1 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    TSP_CUDA(cudaMemcpyAsync(tile_ptr.data(), dm->tile_ptr.p, nb1 * sizeof(int), cudaMemcpyDeviceToHost, s));
     TSP_CUDA(cudaStreamSynchronize(s));
 
     // ---- 2. greedy byte-bounded chunking over block rows ----
@@ -370,30 +448,30 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
     };
     chunk_off.push_back(0);
     chunk_item0.push_back(0);
-    std::vector<long long> h_pb;
-    std::vector<int> h_nc;
+    std::vector<long long> h_ob;
+    std::vector<int> h_nc, h_oc, h_ws;
     for (int b = 0; b < tilem; b++)
     {
         const int rowlen = b == tilem - 1 ? rowA - (tilem - 1) * TS : TS;
-        const int nt = row_nt[b];
         const int ns = row_s0[b + 1] - row_s0[b];
-        const long long pay_ll = row_pay[b] - 8ll * nt;
+        const long long pay_ll = (long long)ell_group_bytes((uint32_t)row_nsr[b], vs) + row_ob[b];
         ChunkAcc one;
         one.nrows = 1;
-        one.ntiles = (uint32_t)nt;
+        one.ntiles = (uint32_t)row_nt[b];
+        one.nother = (uint32_t)row_no[b];
         one.nside = (uint32_t)ns;
         one.nsiderows = ns > 0 ? 1 : 0;
-        const bool fits_alone = pay_ll < (long long)C && nt < 65536 &&
-                                (one.payload = (uint32_t)pay_ll, one.bytes(vs) <= C) && one.xbytes(vs) <= X;
+        bool fits_alone = pay_ll < (long long)C && row_nt[b] < 60000 && row_nsr[b] < 60000 && ns < (int)C;
+        if (fits_alone)
+        {
+            one.payload = (uint32_t)pay_ll;
+            fits_alone = one.bytes(vs) <= C && one.xbytes(vs) <= X;
+        }
         if (fits_alone)
         {
             ChunkAcc trial = acc;
-            trial.nrows += 1;
-            trial.ntiles += one.ntiles;
-            trial.nside += one.nside;
-            trial.nsiderows += one.nsiderows;
-            trial.payload += one.payload;
-            if (trial.bytes(vs) > C || trial.xbytes(vs) > X || trial.nrows > 65535u)
+            trial.add(one);
+            if (trial.bytes(vs) > C || trial.xbytes(vs) > X || trial.nrows > 4000u)
             {
                 close_chunk();
                 trial = one;
@@ -406,35 +484,49 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
         close_chunk();
         const int ta = tile_ptr[b], tb = tile_ptr[b + 1];
         const int64_t slot0 = nslots;
-        if (nt > 0)
+        if (row_nt[b] > 0)
         {
             const size_t cntt = (size_t)(tb - ta) + 1;
-            h_pb.resize(cntt);
+            h_ob.resize(cntt);
             h_nc.resize(cntt);
-            TSP_CUDA(cudaMemcpyAsync(h_pb.data(), pbscan.as<long long>() + ta, cntt * sizeof(long long), cudaMemcpyDeviceToHost, s));
-            TSP_CUDA(cudaMemcpyAsync(h_nc.data(), ncscan.as<int>() + ta, cntt * sizeof(int), cudaMemcpyDeviceToHost, s));
+            h_oc.resize(cntt);
+            h_ws.resize(cntt);
+            TSP_CUDA(cudaMemcpyAsync(h_ob.data(), d_ob.as<long long>() + ta, cntt * sizeof(long long), cudaMemcpyDeviceToHost, s));
+            TSP_CUDA(cudaMemcpyAsync(h_nc.data(), d_nc.as<int>() + ta, cntt * sizeof(int), cudaMemcpyDeviceToHost, s));
+            TSP_CUDA(cudaMemcpyAsync(h_oc.data(), d_oc.as<int>() + ta, cntt * sizeof(int), cudaMemcpyDeviceToHost, s));
+            TSP_CUDA(cudaMemcpyAsync(h_ws.data(), d_ws.as<int>() + ta, cntt * sizeof(int), cudaMemcpyDeviceToHost, s));
             TSP_CUDA(cudaStreamSynchronize(s));
             int t = ta;
             while (t < tb)
             {
+                // grow the piece [t, te) tile by tile while it still fits
                 int te = t;
-                ChunkAcc piece;
-                piece.nrows = 1;
+                uint32_t p_nt = 0, p_no = 0, p_nsr = 0, p_ob = 0;
                 while (te < tb)
                 {
                     const uint32_t is_tile = (uint32_t)(h_nc[te + 1 - ta] - h_nc[te - ta]);
-                    const uint32_t pb = (uint32_t)(h_pb[te + 1 - ta] - h_pb[te - ta]) - 8u * is_tile;
-                    ChunkAcc trial = piece;
-                    trial.ntiles += is_tile;
-                    trial.payload += pb;
-                    if (is_tile && piece.ntiles > 0 && (trial.bytes(vs) > C || trial.xbytes(vs) > X))
+                    const uint32_t t_no = (uint32_t)(h_oc[te + 1 - ta] - h_oc[te - ta]);
+                    const uint32_t t_nsr = (uint32_t)(h_ws[te + 1 - ta] - h_ws[te - ta]);
+                    const uint32_t t_ob = (uint32_t)(h_ob[te + 1 - ta] - h_ob[te - ta]);
+                    ChunkAcc trial;
+                    trial.nrows = 1;
+                    trial.ntiles = p_nt + is_tile;
+                    trial.nother = p_no + t_no;
+                    trial.payload = ell_group_bytes(p_nsr + t_nsr, vs) + p_ob + t_ob;
+                    if (is_tile && p_nt > 0 && (trial.bytes(vs) > C || trial.xbytes(vs) > X))
                         break;
-                    piece = trial;
+                    p_nt += is_tile;
+                    p_no += t_no;
+                    p_nsr += t_nsr;
+                    p_ob += t_ob;
                     te++;
                 }
-                if (piece.ntiles > 0)
+                if (p_nt > 0)
                 {
-                    acc = piece;
+                    acc.nrows = 1;
+                    acc.ntiles = p_nt;
+                    acc.nother = p_no;
+                    acc.payload = ell_group_bytes(p_nsr, vs) + p_ob;
                     items.push_back(PlanItem{b, t, te, row_s0[b], row_s0[b], ROW_PARTIAL | (uint32_t)nslots, rowlen});
                     nslots++;
                     close_chunk();
@@ -444,7 +536,7 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
         }
         if (ns > 0)
         {
-            const uint32_t fixed = 32u + 8u + 32u + 16u + 16u;
+            const uint32_t fixed = CHUNK_OFF_ROWS + 16u + SIDEHDR_BYTES + 16u + 16u;
             uint32_t max_side = (C - fixed) / (4u + vs);
             if (max_side > X / vs)
                 max_side = X / vs;
@@ -511,8 +603,7 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
         a.items = d_items.as<PlanItem>();
         a.chunk_item0 = d_chunk_item0.as<long long>();
         a.chunk_off = P->chunk_off.as<unsigned long long>();
-        a.pbscan = pbscan.as<long long>();
-        a.ncscan = ncscan.as<int>();
+        a.sc = sc;
         a.stream = P->stream.as<unsigned char>();
         a.error_flag = d_err.as<int>();
         a.rowA = dm->rowA;
@@ -544,7 +635,7 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
         a.side_ptr = dm->deferredcoo_ptr.as<int>();
         a.side_col = dm->deferredcoo_colidx.as<int>();
         a.side_val = dm->deferredcoo_val.as<T>();
-        const size_t shm = (size_t)max_items * 4 * sizeof(int);
+        const size_t shm = (size_t)max_items * PACK_ITEM_INTS * sizeof(int);
         if (shm > 200 * 1024)
         {
             set_error("plan: too many block rows in one chunk");
@@ -585,8 +676,9 @@ int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tiles
     P->nnz = dm->nnz;
     const int vs = dm->precision;
     P->chunk_bytes = opts && opts->chunk_bytes ? opts->chunk_bytes : 4096;
-    P->xstage_bytes = opts && opts->xstage_bytes ? opts->xstage_bytes : (vs == 8 ? 3072 : 2048);
+    P->xstage_bytes = opts && opts->xstage_bytes ? opts->xstage_bytes : (vs == 8 ? 2048 : 1024);
     P->ctas_per_sm = opts ? opts->ctas_per_sm : 0;
+    P->stages = opts ? opts->stages : 0;
     if (P->chunk_bytes < 2560 || P->chunk_bytes > 32768 || (P->chunk_bytes & 127) || P->xstage_bytes < 16 * vs ||
         P->xstage_bytes > 32768 || (P->xstage_bytes & 127))
     {

@@ -25,7 +25,7 @@ struct tilespmv_plan
     tsp::DevBuf split_tab; // int4 {block row, first slot, #slots, rowlen} per split row
 
     // launch configuration of the persistent kernel
-    int grid = 0, block = 0, smem = 0, ctas_per_sm = 0, sm_count = 0;
+    int grid = 0, block = 0, smem = 0, ctas_per_sm = 0, sm_count = 0, stages = 0;
 
     // roofline accounting
     int64_t b_alg = 0, b_csr = 0;

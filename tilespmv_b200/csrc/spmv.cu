@@ -4,17 +4,18 @@
 // buffers of v5 (:5-392) and the three CSR5 kernels used for the extracted side matrix
 // (external/CSR5_cuda/detail/cuda/csr5_spmv_cuda.h:275-420) with ONE kernel:
 //
-//   * persistent grid (ctas_per_sm x #SM CTAs of 4 warps); every warp owns a static, byte-balanced
-//     round-robin slice of the chunk list (chunks are <= chunk_bytes of packed stream, stream.cuh)
-//   * each warp runs its own 3-stage TMA pipeline: one lane issues cp.async.bulk (global -> shared,
-//     completion on an mbarrier) for the chunk two ahead, so the HBM stream stays in flight
+//   * persistent grid (one CTA per SM with as many warps as shared memory holds); every warp owns a
+//     static, byte-balanced round-robin slice of the chunk list (chunks are <= chunk_bytes of packed stream, stream.cuh)
+//   * each warp runs its own 4-stage TMA pipeline: one lane issues cp.async.bulk (global -> shared,
+//     completion on an mbarrier) for the chunk three ahead, so the HBM stream stays in flight
 //     independently of the arithmetic; the matrix bytes are read exactly once, fully coalesced,
 //     16-byte aligned
 //   * the x operand is staged in shared memory one chunk ahead with cp.async (16 B pieces of the
 //     16-element segment each tile needs, 4/8 B gathers for the extracted nonzeros)
-//   * lane L works on local row L&15, half L>>4 takes every other slot / element; the 16 partial
-//     y of a block row live in registers, halves are combined with one shuffle, and y is written
-//     once with a coalesced 128-byte store -- no cudaMemset(d_y), no atomics (the reference needs
+//   * lane L owns local rows 2(L&7), 2(L&7)+1 (one 128-bit shared-memory load fetches both values);
+//     the ELL tiles of a block row are one flat list of 16-value slot-rows, so the inner loop has no
+//     per-tile control flow; the 4 lane groups are combined with two shuffles and y is written once
+//     with a coalesced 128-byte store -- no cudaMemset(d_y), no atomics (the reference needs
 //     both, tilespmv_cuda.h:784-790, :1116)
 //   * block rows cut across chunks write partial sums to a scratch slot; a tiny second kernel adds
 //     them in a fixed order (deterministic)
@@ -27,10 +28,9 @@
 namespace tsp
 {
 
-constexpr int SPMV_WARPS = 4;
-constexpr int SPMV_THREADS = SPMV_WARPS * 32;
-constexpr int SPMV_STAGES = 3;
-constexpr int SPMV_BAR_BYTES = 128; // SPMV_WARPS * SPMV_STAGES mbarriers, padded
+constexpr int SPMV_MAX_WARPS = 16;
+constexpr int SPMV_MAX_STAGES = 4;
+constexpr int SPMV_BAR_BYTES = SPMV_MAX_WARPS * SPMV_MAX_STAGES * 8; // one mbarrier per (warp, stage)
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers (mbarrier, TMA bulk copy, cp.async)
@@ -124,19 +124,19 @@ __device__ __forceinline__ void stage_x(const unsigned char *st, T *xb, const T 
     const ChunkHeader *h = reinterpret_cast<const ChunkHeader *>(st);
     const int ntiles = h->ntiles;
     const int nside = (int)h->nside;
-    const uint2 *tdesc = reinterpret_cast<const uint2 *>(st + h->off_tiledesc);
+    const uint32_t *tilecol = reinterpret_cast<const uint32_t *>(st + CHUNK_OFF_ROWS + 16u * h->nrows);
     const uint32_t *sidecol = reinterpret_cast<const uint32_t *>(st + h->off_sidecol);
-    constexpr int VPP = 16 / (int)sizeof(T);  // values per 16-byte piece
-    constexpr int PIECES = TS / VPP;          // pieces per 16-element segment
+    constexpr int VPP = 16 / (int)sizeof(T); // values per 16-byte piece
+    constexpr int PIECES = TS / VPP;         // pieces per 16-element segment
     const uint32_t xb_s = smem_u32(xb);
     for (int i = lane; i < ntiles * PIECES; i += 32)
     {
         const int t = i / PIECES, pc = i % PIECES;
-        const long long col0 = (long long)tdesc[t].x * TS + pc * VPP;
+        const long long col0 = (long long)tilecol[t] * TS + pc * VPP;
         long long left = (long long)colA - col0; // columns of this piece that exist
         left = left < 0 ? 0 : (left > VPP ? VPP : left);
         const T *src = x + (left > 0 ? col0 : 0);
-        cp_async_16(xb_s + (uint32_t)((t * TS + pc * VPP) * (int)sizeof(T)), src, (uint32_t)left * (uint32_t)sizeof(T));
+        cp_async_16(xb_s + (uint32_t)i * 16u, src, (uint32_t)left * (uint32_t)sizeof(T));
     }
     const uint32_t xs_s = xb_s + (uint32_t)(ntiles * TS * (int)sizeof(T));
     for (int e = lane; e < nside; e += 32)
@@ -149,106 +149,149 @@ __device__ __forceinline__ void stage_x(const unsigned char *st, T *xb, const T 
     }
 }
 
+template <class T>
+struct Vec2;
+template <>
+struct Vec2<double>
+{
+    typedef double2 type;
+};
+template <>
+struct Vec2<float>
+{
+    typedef float2 type;
+};
+
 // ---------------------------------------------------------------------------------------------
-// one chunk: all block rows (or row pieces) it holds
+// one chunk: all block rows (or row pieces) it holds.
+// Lane mapping: p = lane & 7 owns local rows 2p and 2p+1 (accumulators a0 / a1); g = lane >> 3
+// selects every 4th slot-row / element, so a warp covers 4 slot-rows (64 values) per iteration
+// with one 128-bit shared-memory load per lane.
 // ---------------------------------------------------------------------------------------------
 template <class T>
 __device__ __forceinline__ void process_chunk(const unsigned char *st, const T *xb, const SpmvArgs<T> &a, int lane)
 {
+    typedef typename Vec2<T>::type V2;
     const ChunkHeader h = *reinterpret_cast<const ChunkHeader *>(st);
-    const uint2 *rows = reinterpret_cast<const uint2 *>(st + 32);
-    const uint2 *tdesc = reinterpret_cast<const uint2 *>(st + h.off_tiledesc);
-    const uint16_t *sidecnt = reinterpret_cast<const uint16_t *>(st + h.off_sidecnt);
+    const uint4 *rows = reinterpret_cast<const uint4 *>(st + CHUNK_OFF_ROWS);
+    const uint2 *odesc = reinterpret_cast<const uint2 *>(st + h.off_odesc);
+    const unsigned char *sidehdr = st + h.off_sidehdr;
     const T *sideval = reinterpret_cast<const T *>(st + h.off_sideval);
     const unsigned char *pay = st + h.off_payload;
     const T *xside = xb + (int)h.ntiles * TS;
-    const int r = lane & 15, hsel = lane >> 4;
-    const unsigned half_mask = hsel ? 0xffff0000u : 0x0000ffffu;
-    int ti = 0, so = 0;
+    const int p = lane & 7, g = lane >> 3;
+    const int nrows = (int)h.nrows;
 
-    for (int rr = 0; rr < (int)h.nrows; rr++)
+    for (int rr = 0; rr < nrows; rr++)
     {
-        const uint2 rec = rows[rr];
-        const int nt = (int)(rec.y & 0xffffu);
-        const int rowlen = (int)((rec.y >> 16) & 0xffu);
-        T acc = 0;
-        for (int t = 0; t < nt; t++, ti++)
+        const uint4 rec = rows[rr];
+        const int nsr = (int)(rec.y & 0xffffu);
+        const int nother = (int)(rec.y >> 16);
+        const int rowlen = (int)(rec.z & 0xffu);
+        const unsigned flags = (rec.z >> 8) & 0xffu;
+        T a0 = 0, a1 = 0;
+
+        // ---- ELL group: one flat loop over the slot-rows of all ELL tiles of the row ----
         {
-            const uint2 d = tdesc[ti];
-            const int fmt = (int)(d.y & 0xffu);
-            const int w = (int)((d.y >> 8) & 0xffu);
-            const int aux = (int)(d.y >> 16);
-            const T *xs = xb + ti * TS;
+            const V2 *vals = reinterpret_cast<const V2 *>(pay);
+            const unsigned char *idx = pay + nsr * TS * (int)sizeof(T);
+            const unsigned char *xsel = idx + nsr * 8;
+#pragma unroll 2
+            for (int sr = g; sr < nsr; sr += 4)
+            {
+                const V2 v = vals[sr * 8 + p];
+                const unsigned b = idx[sr * 8 + p];
+                const T *xs = xb + (int)xsel[sr] * TS;
+                const T x0 = xs[b >> 4], x1 = xs[b & 15u];
+                if (v.x != (T)0) // stored zeros are skipped like tilespmv_cpu.h:182
+                    a0 = fma_t<T>(v.x, x0, a0);
+                if (v.y != (T)0)
+                    a1 = fma_t<T>(v.y, x1, a1);
+            }
+            pay += nsr * TS * (int)sizeof(T) + (int)pad16((uint32_t)nsr * 9u);
+        }
+
+        // ---- the other tiles of the row ----
+        for (int t = 0; t < nother; t++)
+        {
+            const uint2 d = *odesc++;
+            const int fmt = (int)(d.x & 0xffu);
+            const T *xs = xb + (int)((d.x >> 8) & 0xffu) * TS;
+            const int w = (int)(d.x >> 16);
             const T *vals = reinterpret_cast<const T *>(pay);
             switch (fmt)
             {
-            case TILESPMV_FMT_ELL:
-            case TILESPMV_FMT_HYB:
-            {
-                const unsigned char *idx = pay + w * TS * (int)sizeof(T);
-                for (int s = hsel; s < w; s += 2)
-                {
-                    const int e = s * TS + r;
-                    const T v = vals[e];
-                    const unsigned b = idx[e >> 1];
-                    const unsigned c = (r & 1) ? (b & 15u) : (b >> 4);
-                    if (v != (T)0) // stored zeros are skipped like tilespmv_cpu.h:182
-                        acc = fma_t<T>(v, xs[c], acc);
-                }
-                pay += w * TS * (int)sizeof(T) + w * 8;
-                break;
-            }
             case TILESPMV_FMT_CSR:
             {
-                const int nnz = aux;
+                const int nnz = (int)d.y;
                 const unsigned char *ptr = pay;
                 const T *cv = reinterpret_cast<const T *>(pay + 16);
                 const uint32_t vbytes = pad8((uint32_t)nnz * (uint32_t)sizeof(T));
                 const unsigned char *idx = pay + 16 + vbytes;
-                const int start = ptr[r];
-                const int end = r == TS - 1 ? nnz : (int)ptr[r + 1];
-                for (int k = start + hsel; k < end; k += 2)
+                const int s0 = ptr[2 * p], s1 = ptr[2 * p + 1];
+                const int e1 = p == 7 ? nnz : (int)ptr[2 * p + 2];
+                for (int k = s0 + g; k < s1; k += 4)
                 {
                     const unsigned b = idx[k >> 1];
-                    const unsigned c = (k & 1) ? (b & 15u) : (b >> 4);
-                    acc = fma_t<T>(cv[k], xs[c], acc);
+                    a0 = fma_t<T>(cv[k], xs[(k & 1) ? (b & 15u) : (b >> 4)], a0);
                 }
-                pay += 16 + vbytes + pad8(((uint32_t)nnz + 1u) / 2u);
+                for (int k = s1 + g; k < e1; k += 4)
+                {
+                    const unsigned b = idx[k >> 1];
+                    a1 = fma_t<T>(cv[k], xs[(k & 1) ? (b & 15u) : (b >> 4)], a1);
+                }
+                pay += pad16(16u + vbytes + pad8(((uint32_t)nnz + 1u) / 2u));
                 break;
             }
             case TILESPMV_FMT_DENSE:
             {
+                const V2 *dv = reinterpret_cast<const V2 *>(pay);
 #pragma unroll
-                for (int c = 0; c < TS; c += 2)
-                    acc = fma_t<T>(vals[(c + hsel) * TS + r], xs[c + hsel], acc);
+                for (int c = 0; c < TS; c += 4)
+                {
+                    const V2 v = dv[(c + g) * 8 + p];
+                    const T xc = xs[c + g];
+                    a0 = fma_t<T>(v.x, xc, a0);
+                    a1 = fma_t<T>(v.y, xc, a1);
+                }
                 pay += TS * TS * (int)sizeof(T);
                 break;
             }
             case TILESPMV_FMT_DENSECOL:
             {
+                const V2 *dv = reinterpret_cast<const V2 *>(pay);
                 const unsigned long long ids = *reinterpret_cast<const unsigned long long *>(pay + w * TS * (int)sizeof(T));
-                for (int k = hsel; k < w; k += 2)
+                for (int k = g; k < w; k += 4)
                 {
-                    const unsigned c = (unsigned)(ids >> (4 * k)) & 15u;
-                    acc = fma_t<T>(vals[k * TS + r], xs[c], acc);
+                    const V2 v = dv[k * 8 + p];
+                    const T xc = xs[(unsigned)(ids >> (4 * k)) & 15u];
+                    a0 = fma_t<T>(v.x, xc, a0);
+                    a1 = fma_t<T>(v.y, xc, a1);
                 }
-                pay += w * TS * (int)sizeof(T) + 8;
+                pay += pad16((uint32_t)(w * TS) * (uint32_t)sizeof(T) + 8u);
                 break;
             }
             case TILESPMV_FMT_DENSEROW:
             {
-                // half-warp per dense row: lane = column, 16-lane tree sum, result to the row's lane
-                const unsigned mask = (unsigned)aux;
+                // half-warp per dense row: lane = column, 16-lane tree sum, result to the row's owner
+                const unsigned mask = d.y;
+                const int hsel = lane >> 4, c = lane & 15;
+                const unsigned half_mask = hsel ? 0xffff0000u : 0x0000ffffu;
                 for (int i = hsel; i < w; i += 2)
                 {
-                    T p = vals[i * TS + r] * xs[r];
-                    p += __shfl_xor_sync(half_mask, p, 8);
-                    p += __shfl_xor_sync(half_mask, p, 4);
-                    p += __shfl_xor_sync(half_mask, p, 2);
-                    p += __shfl_xor_sync(half_mask, p, 1);
+                    T pr = vals[i * TS + c] * xs[c];
+                    pr += __shfl_xor_sync(half_mask, pr, 8);
+                    pr += __shfl_xor_sync(half_mask, pr, 4);
+                    pr += __shfl_xor_sync(half_mask, pr, 2);
+                    pr += __shfl_xor_sync(half_mask, pr, 1);
                     const int target = (int)__fns(mask, 0, i + 1);
-                    if (r == target)
-                        acc += p;
+                    if (c == (target >> 1)) // lanes (p = target/2, g = 2*hsel): g is 0 or 2 for c < 8
+                    {
+                        if (target & 1)
+                            a1 += pr;
+                        else
+                            a0 += pr;
+                    }
                 }
                 pay += w * TS * (int)sizeof(T);
                 break;
@@ -257,53 +300,68 @@ __device__ __forceinline__ void process_chunk(const unsigned char *st, const T *
                 break;
             }
         }
-        if ((rec.y >> 24) & ROWF_HAS_SIDE)
+
+        // ---- extracted very-sparse nonzeros of this block row: 4 lanes per row pair ----
+        if (flags & ROWF_HAS_SIDE)
         {
-            // extracted very-sparse nonzeros of this block row: 2 lanes per row
-            const int cnt = (int)sidecnt[r];
-            sidecnt += TS;
-            int incl = cnt;
-#pragma unroll
-            for (int dd = 1; dd < TS; dd <<= 1)
-            {
-                int o = __shfl_up_sync(0xffffffffu, incl, dd, TS);
-                if (r >= dd)
-                    incl += o;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, TS - 1, TS);
-            const int end = so + incl;
-            for (int e = end - cnt + hsel; e < end; e += 2)
-                acc = fma_t<T>(sideval[e], xside[e], acc);
-            so += total;
+            const uint16_t *sh = reinterpret_cast<const uint16_t *>(sidehdr);
+            sidehdr += SIDEHDR_BYTES;
+            const int s0 = sh[2 * p], s1 = sh[2 * p + 1], e1 = sh[2 * p + 2];
+            for (int e = s0 + g; e < s1; e += 4)
+                a0 = fma_t<T>(sideval[e], xside[e], a0);
+            for (int e = s1 + g; e < e1; e += 4)
+                a1 = fma_t<T>(sideval[e], xside[e], a1);
+            const int total = sh[16];
+            sideval += total;
+            xside += total;
         }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-        if (lane < rowlen)
+
+        // ---- combine the 4 lane groups, lanes 0..7 store rows (2p, 2p+1) with one 16-byte store ----
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 8);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 8);
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+        if (lane < 8 && 2 * lane < rowlen)
         {
-            if (rec.x & ROW_PARTIAL)
-                a.scratch[(size_t)(rec.x & ~ROW_PARTIAL) * TS + lane] = acc;
-            else
+            const bool partial = (rec.x & ROW_PARTIAL) != 0;
+            const size_t row = (size_t)(rec.x & ~ROW_PARTIAL) * TS + 2 * lane;
+            T *dst = (partial ? a.scratch : a.y) + row;
+            if (2 * lane + 1 < rowlen)
             {
-                const size_t row = (size_t)rec.x * TS + lane;
-                a.y[row] = acc;
-                for (int p = 0; p < a.npeers; p++) // fused all-gather: next x of every peer
-                    a.peers[p][a.row_offset + (long long)row] = acc;
+                V2 o;
+                o.x = a0;
+                o.y = a1;
+                *reinterpret_cast<V2 *>(dst) = o;
             }
+            else
+                dst[0] = a0;
+            if (!partial)
+                for (int q = 0; q < a.npeers; q++) // fused all-gather: next x of every peer
+                {
+                    T *px = a.peers[q] + a.row_offset + (long long)row;
+                    px[0] = a0;
+                    if (2 * lane + 1 < rowlen)
+                        px[1] = a1;
+                }
         }
     }
 }
 
-template <class T>
-__global__ void __launch_bounds__(SPMV_THREADS) tile_spmv_kernel(const SpmvArgs<T> a)
+template <class T, int SPMV_STAGES>
+__global__ void __launch_bounds__(SPMV_MAX_WARPS * 32, 1) tile_spmv_kernel(const SpmvArgs<T> a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps_cta = blockDim.x >> 5;
     const uint32_t per_warp = (uint32_t)(SPMV_STAGES * a.chunk_bytes + 2 * a.xstage_bytes);
     unsigned char *wbase = smem + SPMV_BAR_BYTES + (size_t)warp * per_warp;
     unsigned char *xbase = wbase + (size_t)SPMV_STAGES * a.chunk_bytes;
-    const uint32_t bar0 = smem_u32(smem) + (uint32_t)(warp * SPMV_STAGES * 8);
+    const uint32_t bar0 = smem_u32(smem) + (uint32_t)(warp * SPMV_MAX_STAGES * 8);
 
-    const long long gw = (long long)blockIdx.x * SPMV_WARPS + warp;
-    const long long nw = (long long)gridDim.x * SPMV_WARPS;
+    // warp w of CTA b takes chunks gw, gw + nw, ...: neighbouring warps of one SM stream
+    // neighbouring chunks
+    const long long gw = (long long)blockIdx.x * nwarps_cta + warp;
+    const long long nw = (long long)gridDim.x * nwarps_cta;
     const long long nk = gw < a.nchunks ? (a.nchunks - gw + nw - 1) / nw : 0;
     if (nk == 0)
         return;
@@ -385,44 +443,59 @@ __global__ void __launch_bounds__(128)
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static size_t cta_smem_bytes(const tilespmv_plan *P)
+static size_t warp_smem_bytes(const tilespmv_plan *P)
 {
-    return (size_t)SPMV_BAR_BYTES + (size_t)SPMV_WARPS * ((size_t)SPMV_STAGES * P->chunk_bytes + 2 * (size_t)P->xstage_bytes);
+    return (size_t)P->stages * P->chunk_bytes + 2 * (size_t)P->xstage_bytes;
 }
 
+template <class T>
+static int set_kernel_attrs(int stages, int smem)
+{
+    const void *fn = stages == 2   ? (const void *)tile_spmv_kernel<T, 2>
+                     : stages == 3 ? (const void *)tile_spmv_kernel<T, 3>
+                                   : (const void *)tile_spmv_kernel<T, 4>;
+    TSP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TSP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    return TILESPMV_OK;
+}
+
+// One persistent CTA per SM (ctas_per_sm can raise it); the CTA gets as many independent warps as
+// its shared memory holds -- every warp owns SPMV_STAGES chunk buffers + 2 x-staging buffers.
 int spmv_configure(tilespmv_plan *P)
 {
     int dev = 0;
     TSP_CUDA(cudaGetDevice(&dev));
-    int sms = 0, smem_sm = 0, smem_optin = 0;
+    int sms = 0, smem_optin = 0;
     TSP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    TSP_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
     TSP_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const size_t smem = cta_smem_bytes(P);
-    if (smem > (size_t)smem_optin)
+    if (P->ctas_per_sm <= 0)
+        P->ctas_per_sm = 1;
+    if (P->stages < 2 || P->stages > SPMV_MAX_STAGES)
+        P->stages = 4;
+    if (P->ctas_per_sm > 8)
+        P->ctas_per_sm = 8;
+    const size_t budget = ((size_t)smem_optin + 1024) / P->ctas_per_sm - 1024; // 1 KB per CTA is reserved
+    const size_t per_warp = warp_smem_bytes(P);
+    if (budget < SPMV_BAR_BYTES + per_warp)
     {
-        set_error("plan: chunk_bytes/xstage_bytes need %zu B of shared memory per CTA, device allows %d", smem, smem_optin);
+        set_error("plan: chunk_bytes/xstage_bytes need %zu B of shared memory per warp, only %zu available",
+                  per_warp, budget - SPMV_BAR_BYTES);
         return TILESPMV_ERR_INVALID;
     }
-    int fit = (int)((size_t)smem_sm / (smem + 1024)); // 1 KB per CTA is reserved by the driver
-    if (fit < 1)
-        fit = 1;
-    if (P->ctas_per_sm <= 0 || P->ctas_per_sm > fit)
-        P->ctas_per_sm = fit;
+    int warps = (int)((budget - SPMV_BAR_BYTES) / per_warp);
+    if (warps > SPMV_MAX_WARPS / P->ctas_per_sm)
+        warps = SPMV_MAX_WARPS / P->ctas_per_sm;
+    if (warps < 1)
+        warps = 1;
+    const size_t smem = SPMV_BAR_BYTES + (size_t)warps * per_warp;
     P->sm_count = sms;
     P->grid = sms * P->ctas_per_sm;
-    P->block = SPMV_THREADS;
+    P->block = warps * 32;
     P->smem = (int)smem;
     if (P->precision == 8)
-    {
-        TSP_CUDA(cudaFuncSetAttribute(tile_spmv_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TSP_CUDA(cudaFuncSetAttribute(tile_spmv_kernel<double>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    }
+        TSP_TRY(set_kernel_attrs<double>(P->stages, (int)smem));
     else
-    {
-        TSP_CUDA(cudaFuncSetAttribute(tile_spmv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TSP_CUDA(cudaFuncSetAttribute(tile_spmv_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    }
+        TSP_TRY(set_kernel_attrs<float>(P->stages, (int)smem));
     return TILESPMV_OK;
 }
 
@@ -445,12 +518,17 @@ static int plan_launch_t(tilespmv_plan *P, const T *x, T *y, cudaStream_t s)
     a.row_offset = P->row_offset;
     for (int p = 0; p < TSP_MAX_PEERS; p++)
         a.peers[p] = reinterpret_cast<T *>(P->peers[p]);
-    long long warps_needed = P->nchunks;
+    const int warps = P->block / 32;
     int grid = P->grid;
-    const long long ctas_needed = (warps_needed + SPMV_WARPS - 1) / SPMV_WARPS;
+    const long long ctas_needed = (P->nchunks + warps - 1) / warps;
     if (ctas_needed < grid)
         grid = (int)ctas_needed;
-    TSP_LAUNCH((tile_spmv_kernel<T>), grid, SPMV_THREADS, (size_t)P->smem, s, a);
+    if (P->stages == 2)
+        TSP_LAUNCH((tile_spmv_kernel<T, 2>), grid, P->block, (size_t)P->smem, s, a);
+    else if (P->stages == 3)
+        TSP_LAUNCH((tile_spmv_kernel<T, 3>), grid, P->block, (size_t)P->smem, s, a);
+    else
+        TSP_LAUNCH((tile_spmv_kernel<T, 4>), grid, P->block, (size_t)P->smem, s, a);
     if (P->nsplit > 0)
     {
         const long long threads = P->nsplit * TS;

@@ -5,21 +5,25 @@
 // contiguous stream cut into scheduler chunks of <= chunk_bytes, each 16-byte aligned so that a
 // warp fetches its whole chunk with a single TMA bulk copy (cp.async.bulk) into shared memory:
 //
-//   ChunkHeader                         32 B
-//   RowRec   [nrows]                     8 B each   block rows (or pieces of long block rows)
-//   TileDesc [ntiles]                    8 B each   tile column, format, width, aux
-//   SideCnt  [#rows with side][16] u16  32 B each   per-row counts of extracted (COO-tile) nonzeros
+//   ChunkHeader                          32 B
+//   RowRec   [nrows]                     16 B each  block rows (or pieces of long block rows)
+//   TileCol  [ntiles] u32                pad 8      tile column of every stream tile (x staging)
+//   ODesc    [nother]                     8 B each  descriptors of the non-ELL tiles
+//   SideHdr  [#rows with side][20] u16   40 B each  17 exclusive row starts of the extracted nnz
 //   SideCol  [nside] u32                 pad 8      GLOBAL columns of the extracted nonzeros
 //   SideVal  [nside] T                   pad 8
-//   payload of every tile, in order, each padded to 8 B:
-//     CSR      : rowstart[16] u8 | val[nnz] T (pad 8) | nibbles ceil(nnz/2) (pad 8)
-//     ELL/HYB  : val[w][16] T (slot-major, rows padded to 16) | nibbles[w][16] -> w*8 B
-//     Dense    : val[16][16] T column-major (padded)
-//     DenseRow : val[ndr][16] T row-major (padded); row ids as a 16-bit mask in the descriptor
-//     DenseCol : val[ndc][16] T slot-major | 16 column nibbles in one u64
+//   payload, row after row:
+//     ELL group of the row -- ALL slot-rows (16 values, one per local row) of its ELL/HYB tiles,
+//     flattened so the kernel runs one branch-free loop over them:
+//         val [nsr][16] T | nibbles [nsr][8] B | xsel [nsr] u8 (x segment of the slot-row), pad 16
+//     then the other tiles of the row in order, each padded to 16 B:
+//         CSR      : rowstart[16] u8 | val[nnz] T (pad 8) | nibbles ceil(nnz/2) (pad 8)
+//         Dense    : val[16][16] T column-major (rows / columns padded with zeros)
+//         DenseRow : val[ndr][16] T row-major (padded); row ids as a 16-bit mask in the descriptor
+//         DenseCol : val[ndc][16] T slot-major | 16 column nibbles in one u64
 //   pad to 16
-// Nibble parity is TILE-LOCAL here (element e of a tile sits in byte e/2, high nibble when e is
-// even); the reference's global-position parity (csr2tile.h:973, :982) only exists in Tile_matrix.
+// Nibble parity is TILE-LOCAL here (element e sits in byte e/2, high nibble when e is even); the
+// reference's global-position parity (csr2tile.h:973, :982) only exists in Tile_matrix.
 // COO tiles are not in the stream as tiles: their nonzeros live in the side part exactly once
 // (SURVEY.md A.6 design (i), fused into the block row's epilogue).
 #pragma once
@@ -31,53 +35,71 @@ namespace tsp
 struct ChunkHeader // 32 B
 {
     uint16_t nrows;
-    uint16_t ntiles;
+    uint16_t ntiles; // stream tiles (ELL + other), = number of staged x segments
     uint32_t nside;
-    uint32_t off_tiledesc;
-    uint32_t off_sidecnt;
+    uint32_t nother;
+    uint32_t off_odesc;
+    uint32_t off_sidehdr;
     uint32_t off_sidecol;
     uint32_t off_sideval;
     uint32_t off_payload;
-    uint32_t total_bytes;
 };
 static_assert(sizeof(ChunkHeader) == 32, "ChunkHeader must be 32 bytes");
+constexpr uint32_t CHUNK_OFF_ROWS = 32;
 
-// RowRec as uint2: x = dest (block row index, or 0x80000000 | partial-sum slot for a piece of a
-// split block row); y = ntiles | rowlen << 16 | flags << 24
+struct RowRec // 16 B
+{
+    uint32_t dest;   // block row index, or ROW_PARTIAL | partial-sum slot for a piece of a split row
+    uint16_t nsr;    // slot-rows in the row's ELL group
+    uint16_t nother; // non-ELL tiles
+    uint8_t rowlen;  // rows that exist (16 except in the last block row)
+    uint8_t flags;   // ROWF_*
+    uint16_t pad0;
+    uint32_t pad1;
+};
+static_assert(sizeof(RowRec) == 16, "RowRec must be 16 bytes");
 constexpr uint32_t ROW_PARTIAL = 0x80000000u;
 constexpr uint32_t ROWF_HAS_SIDE = 1u;
-// TileDesc as uint2: x = tile column; y = format | width << 8 | aux << 16
-//   aux: CSR nnz; DenseRow 16-bit row mask; otherwise 0
+constexpr uint32_t SIDEHDR_BYTES = 40; // 17 x u16 used
+
+// ODesc as uint2: x = format | xsel << 8 | width << 16 ; y = aux (CSR nnz, DenseRow row mask)
 
 __host__ __device__ inline uint32_t pad8(uint32_t b) { return (b + 7u) & ~7u; }
 __host__ __device__ inline uint32_t pad16(uint32_t b) { return (b + 15u) & ~15u; }
 
-// payload bytes of one tile (format f, stored per the table above); vs = sizeof(value)
-__host__ __device__ inline uint32_t tile_payload_bytes(int f, int nnz, int width, int nd, uint32_t vs)
+__host__ __device__ inline bool fmt_is_ell(int f) { return f == 2 || f == 3; }
+__host__ __device__ inline bool fmt_is_other(int f) { return f == 0 || f == 4 || f == 5 || f == 6; }
+
+// payload bytes of one non-ELL stream tile; vs = sizeof(value)
+__host__ __device__ inline uint32_t other_payload_bytes(int f, int nnz, int nd, uint32_t vs)
 {
-    switch (f)
+    switch (f) // every payload is padded to 16 B so that 128-bit shared-memory loads stay aligned
     {
     case 0: // CSR
-        return 16u + pad8((uint32_t)nnz * vs) + pad8(((uint32_t)nnz + 1u) / 2u);
-    case 2: // ELL
-    case 3: // HYB (ELL part)
-        return (uint32_t)width * 16u * vs + (uint32_t)width * 8u;
+        return pad16(16u + pad8((uint32_t)nnz * vs) + pad8(((uint32_t)nnz + 1u) / 2u));
     case 4: // Dense
         return 256u * vs;
     case 5: // DenseRow
         return (uint32_t)nd * 16u * vs;
     case 6: // DenseCol
-        return (uint32_t)nd * 16u * vs + 8u;
-    default: // COO: lives in the side part
+        return pad16((uint32_t)nd * 16u * vs + 8u);
+    default:
         return 0u;
     }
 }
-
-// total size of a chunk from its counters (must match pack_kernel's layout exactly)
-__host__ __device__ inline uint32_t chunk_layout_bytes(uint32_t nrows, uint32_t ntiles, uint32_t nsiderows,
-                                                       uint32_t nside, uint32_t payload, uint32_t vs)
+// bytes of a row's ELL group with nsr slot-rows
+__host__ __device__ inline uint32_t ell_group_bytes(uint32_t nsr, uint32_t vs)
 {
-    return pad16(32u + 8u * nrows + 8u * ntiles + 32u * nsiderows + pad8(4u * nside) + pad8(vs * nside) + payload);
+    return nsr * 16u * vs + pad16(nsr * 9u); // values | 8 B of nibbles + 1 B xsel per slot-row
+}
+
+// total size of a chunk from its counters (must match pack_kernel's layout exactly); `payload`
+// = sum over rows of ell_group_bytes + other payloads
+__host__ __device__ inline uint32_t chunk_layout_bytes(uint32_t nrows, uint32_t ntiles, uint32_t nother,
+                                                       uint32_t nsiderows, uint32_t nside, uint32_t payload, uint32_t vs)
+{
+    return pad16(CHUNK_OFF_ROWS + 16u * nrows + pad8(4u * ntiles) + 8u * nother + SIDEHDR_BYTES * nsiderows +
+                 pad8(4u * nside) + pad8(vs * nside)) + payload; // payload parts are multiples of 16
 }
 
 // one schedulable unit: a whole block row, or a piece of a long one
