@@ -30,7 +30,8 @@ namespace tsp
 
 constexpr int SPMV_MAX_WARPS = 16;
 constexpr int SPMV_MAX_STAGES = 4;
-constexpr int SPMV_BAR_BYTES = SPMV_MAX_WARPS * SPMV_MAX_STAGES * 8; // one mbarrier per (warp, stage)
+constexpr int SPMV_BARS_PER_WARP = SPMV_MAX_STAGES + 2;            // chunk stages + 2 x-staging buffers
+constexpr int SPMV_BAR_BYTES = SPMV_MAX_WARPS * SPMV_BARS_PER_WARP * 8 + 256; // padded to 128 B
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers (mbarrier, TMA bulk copy, cp.async)
@@ -116,29 +117,51 @@ struct SpmvArgs
 };
 
 // ---------------------------------------------------------------------------------------------
-// x staging for one chunk (issued one chunk ahead of its use)
+// x staging for one chunk (issued one chunk ahead of its use):
+//   * the 16-element x segment of every stream tile: ONE TMA bulk copy per tile, issued by lane t
+//     for tile t (a single warp instruction stages up to 32 segments), completion on `xbar`
+//   * the x values of the extracted nonzeros: one 8 B / 4 B cp.async gather per nonzero
+// A segment that sticks out past colA (last tile column of a matrix whose width is not a multiple
+// of 16) is staged element-wise with zero fill by its lane instead.
 // ---------------------------------------------------------------------------------------------
 template <class T>
-__device__ __forceinline__ void stage_x(const unsigned char *st, T *xb, const T *__restrict__ x, int colA, int lane)
+__device__ __forceinline__ void stage_x(const unsigned char *st, T *xb, uint32_t xbar, const T *__restrict__ x,
+                                        int colA, int lane)
 {
     const ChunkHeader *h = reinterpret_cast<const ChunkHeader *>(st);
     const int ntiles = h->ntiles;
     const int nside = (int)h->nside;
     const uint32_t *tilecol = reinterpret_cast<const uint32_t *>(st + CHUNK_OFF_ROWS + 16u * h->nrows);
     const uint32_t *sidecol = reinterpret_cast<const uint32_t *>(st + h->off_sidecol);
-    constexpr int VPP = 16 / (int)sizeof(T); // values per 16-byte piece
-    constexpr int PIECES = TS / VPP;         // pieces per 16-element segment
     const uint32_t xb_s = smem_u32(xb);
-    for (int i = lane; i < ntiles * PIECES; i += 32)
+    constexpr uint32_t SEG = TS * (uint32_t)sizeof(T);
+    // pass 1: how many full segments (bytes the barrier has to expect)
+    uint32_t nfull = 0;
+#pragma unroll 1
+    for (int t0 = 0; t0 < ntiles; t0 += 32)
     {
-        const int t = i / PIECES, pc = i % PIECES;
-        const long long col0 = (long long)tilecol[t] * TS + pc * VPP;
-        long long left = (long long)colA - col0; // columns of this piece that exist
-        left = left < 0 ? 0 : (left > VPP ? VPP : left);
-        const T *src = x + (left > 0 ? col0 : 0);
-        cp_async_16(xb_s + (uint32_t)i * 16u, src, (uint32_t)left * (uint32_t)sizeof(T));
+        const int t = t0 + lane;
+        const bool full = t < ntiles && (int)(tilecol[t] * TS + TS) <= colA;
+        nfull += __popc(__ballot_sync(0xffffffffu, full));
     }
-    const uint32_t xs_s = xb_s + (uint32_t)(ntiles * TS * (int)sizeof(T));
+    if (lane == 0)
+        mbar_expect_tx(xbar, nfull * SEG);
+    __syncwarp();
+#pragma unroll 1
+    for (int t = lane; t < ntiles; t += 32)
+    {
+        const int col0 = (int)(tilecol[t] * TS);
+        if (col0 + TS <= colA)
+            tma_load_1d(xb_s + (uint32_t)t * SEG, x + col0, SEG, xbar);
+        else
+        {
+#pragma unroll 1
+            for (int c = 0; c < TS; c++)
+                xb[t * TS + c] = col0 + c < colA ? x[col0 + c] : (T)0;
+        }
+    }
+    const uint32_t xs_s = xb_s + (uint32_t)ntiles * SEG;
+#pragma unroll 1
     for (int e = lane; e < nside; e += 32)
     {
         const T *src = x + sidecol[e];
@@ -202,11 +225,10 @@ __device__ __forceinline__ void process_chunk(const unsigned char *st, const T *
                 const V2 v = vals[sr * 8 + p];
                 const unsigned b = idx[sr * 8 + p];
                 const T *xs = xb + (int)xsel[sr] * TS;
-                const T x0 = xs[b >> 4], x1 = xs[b & 15u];
-                if (v.x != (T)0) // stored zeros are skipped like tilespmv_cpu.h:182
-                    a0 = fma_t<T>(v.x, x0, a0);
-                if (v.y != (T)0)
-                    a1 = fma_t<T>(v.y, x1, a1);
+                // padding slots hold value 0 / column 0 and are multiplied through like in the
+                // reference GPU kernel (tilespmv_cuda.h:597-598); only tilespmv_cpu.h:182 skips them
+                a0 = fma_t<T>(v.x, xs[b >> 4], a0);
+                a1 = fma_t<T>(v.y, xs[b & 15u], a1);
             }
             pay += nsr * TS * (int)sizeof(T) + (int)pad16((uint32_t)nsr * 9u);
         }
@@ -230,11 +252,13 @@ __device__ __forceinline__ void process_chunk(const unsigned char *st, const T *
                 const unsigned char *idx = pay + 16 + vbytes;
                 const int s0 = ptr[2 * p], s1 = ptr[2 * p + 1];
                 const int e1 = p == 7 ? nnz : (int)ptr[2 * p + 2];
+#pragma unroll 1
                 for (int k = s0 + g; k < s1; k += 4)
                 {
                     const unsigned b = idx[k >> 1];
                     a0 = fma_t<T>(cv[k], xs[(k & 1) ? (b & 15u) : (b >> 4)], a0);
                 }
+#pragma unroll 1
                 for (int k = s1 + g; k < e1; k += 4)
                 {
                     const unsigned b = idx[k >> 1];
@@ -307,8 +331,10 @@ __device__ __forceinline__ void process_chunk(const unsigned char *st, const T *
             const uint16_t *sh = reinterpret_cast<const uint16_t *>(sidehdr);
             sidehdr += SIDEHDR_BYTES;
             const int s0 = sh[2 * p], s1 = sh[2 * p + 1], e1 = sh[2 * p + 2];
+#pragma unroll 1
             for (int e = s0 + g; e < s1; e += 4)
                 a0 = fma_t<T>(sideval[e], xside[e], a0);
+#pragma unroll 1
             for (int e = s1 + g; e < e1; e += 4)
                 a1 = fma_t<T>(sideval[e], xside[e], a1);
             const int total = sh[16];
@@ -356,62 +382,83 @@ __global__ void __launch_bounds__(SPMV_MAX_WARPS * 32, 1) tile_spmv_kernel(const
     const uint32_t per_warp = (uint32_t)(SPMV_STAGES * a.chunk_bytes + 2 * a.xstage_bytes);
     unsigned char *wbase = smem + SPMV_BAR_BYTES + (size_t)warp * per_warp;
     unsigned char *xbase = wbase + (size_t)SPMV_STAGES * a.chunk_bytes;
-    const uint32_t bar0 = smem_u32(smem) + (uint32_t)(warp * SPMV_MAX_STAGES * 8);
+    // per warp: SPMV_STAGES barriers for the chunk stream + 2 for the staged x segments
+    const uint32_t bar0 = smem_u32(smem) + (uint32_t)(warp * SPMV_BARS_PER_WARP * 8);
+    const uint32_t xbar0 = bar0 + 8u * SPMV_MAX_STAGES;
 
-    // warp w of CTA b takes chunks gw, gw + nw, ...: neighbouring warps of one SM stream
-    // neighbouring chunks
+    // warp w of CTA b takes chunks gw, gw + nw, ...: neighbouring warps stream neighbouring chunks
     const long long gw = (long long)blockIdx.x * nwarps_cta + warp;
     const long long nw = (long long)gridDim.x * nwarps_cta;
-    const long long nk = gw < a.nchunks ? (a.nchunks - gw + nw - 1) / nw : 0;
+    const int nk = gw < a.nchunks ? (int)((a.nchunks - gw + nw - 1) / nw) : 0;
     if (nk == 0)
         return;
 
     if (lane == 0)
     {
 #pragma unroll
-        for (int st = 0; st < SPMV_STAGES; st++)
-            mbar_init(bar0 + 8u * st, 1);
+        for (int i = 0; i < SPMV_BARS_PER_WARP; i++)
+            mbar_init(bar0 + 8u * i, 1);
         fence_mbar_init();
     }
     __syncwarp();
 
-    auto issue = [&](long long k) { // lane 0 only
-        const long long c = gw + k * nw;
-        const unsigned long long off = a.chunk_off[c];
-        const uint32_t bytes = (uint32_t)(a.chunk_off[c + 1] - off);
-        const int st = (int)(k % SPMV_STAGES);
+    const uint32_t stage0 = smem_u32(wbase);
+    auto issue = [&](int k, unsigned long long off, unsigned long long end) { // lane 0 only
+        const int st = k % SPMV_STAGES;
+        const uint32_t bytes = (uint32_t)(end - off);
         mbar_expect_tx(bar0 + 8u * st, bytes);
-        tma_load_1d(smem_u32(wbase + (size_t)st * a.chunk_bytes), a.stream + off, bytes, bar0 + 8u * st);
+        tma_load_1d(stage0 + (uint32_t)st * (uint32_t)a.chunk_bytes, a.stream + off, bytes, bar0 + 8u * st);
     };
-
+    // lane 0 keeps the offsets of the NEXT chunk to issue in registers, loaded one iteration early
+    unsigned long long nxt_off = 0, nxt_end = 0;
     if (lane == 0)
-        for (long long k = 0; k < SPMV_STAGES && k < nk; k++)
-            issue(k);
+    {
+        for (int k = 0; k < SPMV_STAGES && k < nk; k++)
+        {
+            const long long c = gw + (long long)k * nw;
+            issue(k, a.chunk_off[c], a.chunk_off[c + 1]);
+        }
+        if (SPMV_STAGES < nk)
+        {
+            const long long c = gw + (long long)SPMV_STAGES * nw;
+            nxt_off = a.chunk_off[c];
+            nxt_end = a.chunk_off[c + 1];
+        }
+    }
 
     mbar_wait(bar0, 0);
-    stage_x<T>(wbase, reinterpret_cast<T *>(xbase), a.x, a.colA, lane);
+    stage_x<T>(wbase, reinterpret_cast<T *>(xbase), xbar0, a.x, a.colA, lane);
     cp_async_commit();
 
-    for (long long k = 0; k < nk; k++)
+#pragma unroll 1
+    for (int k = 0; k < nk; k++)
     {
-        const int st = (int)(k % SPMV_STAGES);
+        const int st = k % SPMV_STAGES;
         if (k + 1 < nk)
         {
-            const int st1 = (int)((k + 1) % SPMV_STAGES);
+            const int st1 = (k + 1) % SPMV_STAGES;
             mbar_wait(bar0 + 8u * st1, (uint32_t)(((k + 1) / SPMV_STAGES) & 1));
             stage_x<T>(wbase + (size_t)st1 * a.chunk_bytes,
-                       reinterpret_cast<T *>(xbase + (size_t)((k + 1) & 1) * a.xstage_bytes), a.x, a.colA, lane);
+                       reinterpret_cast<T *>(xbase + (size_t)((k + 1) & 1) * a.xstage_bytes), xbar0 + 8u * ((k + 1) & 1),
+                       a.x, a.colA, lane);
         }
         cp_async_commit();
-        cp_async_wait<1>(); // x of chunk k has landed (this thread's copies) ...
-        __syncwarp();       // ... and everybody else's
+        cp_async_wait<1>();                                          // gathers of chunk k (this thread's) ...
+        mbar_wait(xbar0 + 8u * (k & 1), (uint32_t)((k >> 1) & 1));  // ... its x segments ...
+        __syncwarp();                                                // ... and everybody else's copies
         process_chunk<T>(wbase + (size_t)st * a.chunk_bytes,
                          reinterpret_cast<const T *>(xbase + (size_t)(k & 1) * a.xstage_bytes), a, lane);
-        __syncwarp(); // all lanes are done reading stage st
+        __syncwarp(); // all lanes are done reading stage st and x buffer k&1
         if (lane == 0 && k + SPMV_STAGES < nk)
         {
             fence_proxy_async();
-            issue(k + SPMV_STAGES);
+            issue(k + SPMV_STAGES, nxt_off, nxt_end);
+            if (k + SPMV_STAGES + 1 < nk)
+            {
+                const long long c = gw + (long long)(k + SPMV_STAGES + 1) * nw;
+                nxt_off = a.chunk_off[c];
+                nxt_end = a.chunk_off[c + 1];
+            }
         }
     }
     cp_async_wait<0>();
