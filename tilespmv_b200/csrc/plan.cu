@@ -238,6 +238,8 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long 
 {
     extern __shared__ int s_base[];
     __shared__ ChunkHeader hdr;
+    __shared__ int s_start[TS + 1];
+    __shared__ unsigned s_flags;
     const long long c = blockIdx.x;
     if (c >= nchunks)
         return;
@@ -270,8 +272,9 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long 
             rec.nother = (uint16_t)no;
             rec.rowlen = (uint8_t)it.rowlen;
             rec.flags = (uint8_t)(ns > 0 ? ROWF_HAS_SIDE : 0u);
+            rec.side_nit = 0; // filled in below once the row starts are known
+            rec.ell_bytes16 = (uint16_t)(ell_group_bytes((uint32_t)nsr, vs) / 16u);
             rec.pad0 = 0;
-            rec.pad1 = 0;
             *reinterpret_cast<RowRec *>(out + CHUNK_OFF_ROWS + 16 * k) = rec;
             ntiles += (uint32_t)nt;
             nother += (uint32_t)no;
@@ -281,19 +284,28 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long 
         }
         hdr.nrows = (uint16_t)nitems;
         hdr.ntiles = (uint16_t)ntiles;
-        hdr.nside = nside;
+        hdr.nside = (uint16_t)nside;
+        hdr.flags = 0;
+        const uint32_t off_sidecol = CHUNK_OFF_ROWS + 16u * (uint32_t)nitems + pad16(4u * ntiles);
+        const uint32_t off_odesc = off_sidecol + pad16(4u * nside);
+        const uint32_t off_sidehdr = off_odesc + pad16(8u * nother);
+        const uint32_t off_sideval = off_sidehdr + pad16(SIDEHDR_BYTES * nsiderows);
+        hdr.off_sidecol = (uint16_t)off_sidecol;
+        hdr.off_odesc = (uint16_t)off_odesc;
+        hdr.off_sidehdr = (uint16_t)off_sidehdr;
+        hdr.off_sideval = (uint16_t)off_sideval;
+        hdr.off_payload = off_sideval + pad16(vs * nside);
         hdr.nother = nother;
-        hdr.off_odesc = CHUNK_OFF_ROWS + 16u * (uint32_t)nitems + pad8(4u * ntiles);
-        hdr.off_sidehdr = hdr.off_odesc + 8u * nother;
-        hdr.off_sidecol = hdr.off_sidehdr + SIDEHDR_BYTES * nsiderows;
-        hdr.off_sideval = hdr.off_sidecol + pad8(4u * nside);
-        hdr.off_payload = pad16(hdr.off_sideval + pad8(vs * nside));
+        hdr.pad[0] = hdr.pad[1] = 0;
         *reinterpret_cast<ChunkHeader *>(out) = hdr;
-        if ((unsigned long long)(hdr.off_payload + pay) != a.chunk_off[c + 1] - a.chunk_off[c])
+        if ((unsigned long long)(hdr.off_payload + pay) != a.chunk_off[c + 1] - a.chunk_off[c] || ntiles > 256u ||
+            nside > 0xffffu || hdr.off_payload > 0xffffu)
             atomicExch(a.error_flag, 1);
+        s_flags = 0;
     }
     __syncthreads();
     uint32_t *tilecol = reinterpret_cast<uint32_t *>(out + CHUNK_OFF_ROWS + 16 * nitems);
+    const bool ragged_cols = (a.colA % TS) != 0;
 
     for (int k = 0; k < nitems; k++)
     {
@@ -312,7 +324,10 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long 
             if (f == TILESPMV_FMT_COO)
                 continue;
             const unsigned xsel = (unsigned)(sb[0] + (a.sc.nc[t] - a.sc.nc[it.t0])); // x segment in the chunk
-            tilecol[xsel] = (uint32_t)a.tile_columnidx[t];
+            const int tc = a.tile_columnidx[t];
+            tilecol[xsel] = (uint32_t)tc;
+            if (ragged_cols && tc == a.tilen - 1)
+                atomicOr(&s_flags, CHF_PARTIAL_X);
             if (fmt_is_ell(f))
             {
                 const uint32_t so = (uint32_t)(a.sc.ws[t] - a.sc.ws[it.t0]);
@@ -325,7 +340,7 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long 
                 pack_other_tile<T>(a, t, it.br, xsel, out + hdr.off_odesc + 8u * oi, other_pay + po);
             }
         }
-        const int ns = it.s1 - it.s0;
+        const int ns = it.s1 - it.s0; // uniform across the CTA
         if (ns > 0)
         {
             if (threadIdx.x <= TS)
@@ -340,6 +355,7 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long 
                     lo = lo < it.s1 ? lo : it.s1;
                     st = lo - it.s0;
                 }
+                s_start[r] = st;
                 reinterpret_cast<uint16_t *>(out + hdr.off_sidehdr + SIDEHDR_BYTES * (uint32_t)sb[4])[r] = (uint16_t)st;
             }
             uint32_t *oc = reinterpret_cast<uint32_t *>(out + hdr.off_sidecol) + sb[3];
@@ -349,8 +365,23 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long 
                 oc[e] = (uint32_t)a.side_col[it.s0 + e];
                 ov[e] = a.side_val[it.s0 + e];
             }
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                int nit = 0;
+                for (int r = 0; r < TS; r++)
+                {
+                    const int len = s_start[r + 1] - s_start[r];
+                    nit = max(nit, (len + 3) >> 2);
+                }
+                reinterpret_cast<RowRec *>(out + CHUNK_OFF_ROWS + 16 * k)->side_nit = (uint16_t)nit;
+            }
+            __syncthreads();
         }
     }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_flags)
+        reinterpret_cast<ChunkHeader *>(out)->flags = (uint16_t)s_flags;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -461,7 +492,7 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
         one.nother = (uint32_t)row_no[b];
         one.nside = (uint32_t)ns;
         one.nsiderows = ns > 0 ? 1 : 0;
-        bool fits_alone = pay_ll < (long long)C && row_nt[b] < 60000 && row_nsr[b] < 60000 && ns < (int)C;
+        bool fits_alone = pay_ll < (long long)C && row_nt[b] <= 256 && row_nsr[b] < 60000 && ns < (int)C;
         if (fits_alone)
         {
             one.payload = (uint32_t)pay_ll;
@@ -471,7 +502,7 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
         {
             ChunkAcc trial = acc;
             trial.add(one);
-            if (trial.bytes(vs) > C || trial.xbytes(vs) > X || trial.nrows > 4000u)
+            if (trial.bytes(vs) > C || trial.xbytes(vs) > X || trial.nrows > 1000u || trial.ntiles > 256u)
             {
                 close_chunk();
                 trial = one;
@@ -513,7 +544,7 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
                     trial.ntiles = p_nt + is_tile;
                     trial.nother = p_no + t_no;
                     trial.payload = ell_group_bytes(p_nsr + t_nsr, vs) + p_ob + t_ob;
-                    if (is_tile && p_nt > 0 && (trial.bytes(vs) > C || trial.xbytes(vs) > X))
+                    if (is_tile && p_nt > 0 && (trial.bytes(vs) > C || trial.xbytes(vs) > X || trial.ntiles > 256u))
                         break;
                     p_nt += is_tile;
                     p_no += t_no;
@@ -536,7 +567,7 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
         }
         if (ns > 0)
         {
-            const uint32_t fixed = CHUNK_OFF_ROWS + 16u + SIDEHDR_BYTES + 16u + 16u;
+            const uint32_t fixed = CHUNK_OFF_ROWS + 16u + pad16(SIDEHDR_BYTES) + 16u + 16u; // header, rec, side header, two list paddings
             uint32_t max_side = (C - fixed) / (4u + vs);
             if (max_side > X / vs)
                 max_side = X / vs;
@@ -583,6 +614,18 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
     TSP_TRY(d_items.alloc(items.size() * sizeof(PlanItem), false));
     TSP_TRY(d_chunk_item0.alloc(chunk_item0.size() * sizeof(long long), false));
     TSP_TRY(P->chunk_off.alloc(chunk_off.size() * sizeof(unsigned long long), false));
+    // what the SpMV kernel reads: {offset / 16, bytes} per chunk, one 8-byte load
+    if (off / 16 > 0xffffffffull)
+    {
+        set_error("plan: packed stream larger than 64 GB");
+        return TILESPMV_ERR_UNSUPPORTED;
+    }
+    std::vector<uint2> chunk_desc((size_t)nchunks + 1);
+    for (long long c = 0; c < nchunks; c++)
+        chunk_desc[(size_t)c] = make_uint2((unsigned)(chunk_off[(size_t)c] / 16), (unsigned)(chunk_off[(size_t)c + 1] - chunk_off[(size_t)c]));
+    chunk_desc[(size_t)nchunks] = make_uint2(0u, 0u);
+    TSP_TRY(P->chunk_desc.alloc(chunk_desc.size() * sizeof(uint2), false));
+    TSP_CUDA(cudaMemcpyAsync(P->chunk_desc.p, chunk_desc.data(), chunk_desc.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
     TSP_TRY(P->stream.alloc((size_t)off + 16, true, s));
     TSP_TRY(d_err.alloc(sizeof(int), true, s));
     TSP_TRY(P->scratch.alloc((size_t)nslots * TS * vs, true, s));

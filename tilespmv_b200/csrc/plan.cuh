@@ -16,7 +16,8 @@ struct tilespmv_plan
     int64_t nchunks = 0;
     int64_t stream_bytes = 0;
     tsp::DevBuf stream;    // the packed bytes
-    tsp::DevBuf chunk_off; // uint64[nchunks+1], 16-byte aligned offsets into stream
+    tsp::DevBuf chunk_off; // uint64[nchunks+1], 16-byte aligned offsets into stream (planner / packer)
+    tsp::DevBuf chunk_desc; // uint2[nchunks+1] {offset / 16, bytes}: what the kernel's TMA issue reads
 
     // block rows that were cut across chunks: partial sums land in scratch and are combined by the
     // fix-up kernel in a fixed order (deterministic, no atomics)
@@ -40,7 +41,7 @@ struct tilespmv_plan
 
     int64_t device_bytes() const
     {
-        return (int64_t)(stream.bytes + chunk_off.bytes + scratch.bytes + split_tab.bytes + hx.bytes + hy.bytes);
+        return (int64_t)(stream.bytes + chunk_off.bytes + chunk_desc.bytes + scratch.bytes + split_tab.bytes + hx.bytes + hy.bytes);
     }
 };
 

@@ -30,7 +30,7 @@ namespace tsp
 
 constexpr int SPMV_MAX_WARPS = 16;
 constexpr int SPMV_MAX_STAGES = 4;
-constexpr int SPMV_BARS_PER_WARP = SPMV_MAX_STAGES + 2;            // chunk stages + 2 x-staging buffers
+constexpr int SPMV_BARS_PER_WARP = SPMV_MAX_STAGES;                // one mbarrier per chunk stage
 constexpr int SPMV_BAR_BYTES = SPMV_MAX_WARPS * SPMV_BARS_PER_WARP * 8 + 256; // padded to 128 B
 
 // ---------------------------------------------------------------------------------------------
@@ -74,9 +74,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase)
                      : "memory");
     } while (!done);
 }
-__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src, uint32_t src_bytes)
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_16_zfill(uint32_t dst, const void *src, uint32_t src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_8(uint32_t dst, const void *src)
 {
@@ -100,12 +104,76 @@ __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { 
 template <>
 __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
 
+// explicit shared-state-space loads on 32-bit addresses (the hot loops do their own address
+// arithmetic; ptxas folds constant offsets into the instruction's immediate)
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+// a * b + c in one integer multiply-add (keeps ptxas from expanding nibble * size into shift+mask+add)
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+template <class T>
+struct SL;
+template <>
+struct SL<double>
+{
+    typedef double2 V2;
+    static __device__ __forceinline__ double ld(uint32_t a)
+    {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+        return v;
+    }
+    static __device__ __forceinline__ double2 ld2(uint32_t a)
+    {
+        double2 v;
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+        return v;
+    }
+};
+template <>
+struct SL<float>
+{
+    typedef float2 V2;
+    static __device__ __forceinline__ float ld(uint32_t a)
+    {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+        return v;
+    }
+    static __device__ __forceinline__ float2 ld2(uint32_t a)
+    {
+        float2 v;
+        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+        return v;
+    }
+};
+
 template <class T>
 struct SpmvArgs
 {
     const unsigned char *stream;
-    const unsigned long long *chunk_off;
-    long long nchunks;
+    const uint2 *chunk_desc; // {offset / 16, bytes} per chunk
+    unsigned nchunks;
     const T *x;
     T *y;
     T *scratch;
@@ -117,58 +185,68 @@ struct SpmvArgs
 };
 
 // ---------------------------------------------------------------------------------------------
-// x staging for one chunk (issued one chunk ahead of its use):
-//   * the 16-element x segment of every stream tile: ONE TMA bulk copy per tile, issued by lane t
-//     for tile t (a single warp instruction stages up to 32 segments), completion on `xbar`
-//   * the x values of the extracted nonzeros: one 8 B / 4 B cp.async gather per nonzero
+// x staging for one chunk (issued one chunk ahead of its use), all by cp.async (SASS LDGSTS):
+//   * the 16-element x segment of every stream tile as 16-byte pieces: 8 (fp64) / 4 (fp32) lanes
+//     per segment, so one warp instruction stages 4 / 8 segments, fully coalesced per segment
+//   * the x values of the extracted nonzeros: one 8 B / 4 B gather per nonzero
 // A segment that sticks out past colA (last tile column of a matrix whose width is not a multiple
-// of 16) is staged element-wise with zero fill by its lane instead.
+// of 16) is zero-filled through the src-size operand (chunks flagged CHF_PARTIAL_X only).
+// Completion is tracked by the cp.async group of the calling iteration (no mbarrier).
 // ---------------------------------------------------------------------------------------------
 template <class T>
-__device__ __forceinline__ void stage_x(const unsigned char *st, T *xb, uint32_t xbar, const T *__restrict__ x,
+__device__ __forceinline__ void stage_x(uint32_t st_s, uint32_t xb_s, const T *__restrict__ x, const T *__restrict__ xpiece,
                                         int colA, int lane)
 {
-    const ChunkHeader *h = reinterpret_cast<const ChunkHeader *>(st);
-    const int ntiles = h->ntiles;
-    const int nside = (int)h->nside;
-    const uint32_t *tilecol = reinterpret_cast<const uint32_t *>(st + CHUNK_OFF_ROWS + 16u * h->nrows);
-    const uint32_t *sidecol = reinterpret_cast<const uint32_t *>(st + h->off_sidecol);
-    const uint32_t xb_s = smem_u32(xb);
-    constexpr uint32_t SEG = TS * (uint32_t)sizeof(T);
-    // pass 1: how many full segments (bytes the barrier has to expect)
-    uint32_t nfull = 0;
-#pragma unroll 1
-    for (int t0 = 0; t0 < ntiles; t0 += 32)
+    constexpr int PPT = TS * (int)sizeof(T) / 16; // 16-byte pieces per segment
+    constexpr int TPI = 32 / PPT;                 // segments per warp instruction
+    constexpr int EPP = 16 / (int)sizeof(T);      // elements per piece
+    const uint4 ha = lds_v4(st_s);
+    const int nrows = (int)(ha.x & 0xffffu), ntiles = (int)(ha.x >> 16);
+    const int nside = (int)(ha.y & 0xffffu);
+    const uint32_t tilecol_s = st_s + CHUNK_OFF_ROWS + 16u * (uint32_t)nrows + 4u * (uint32_t)(lane / PPT);
+    const uint32_t sidecol_s = st_s + (ha.z & 0xffffu) + 4u * (uint32_t)lane;
+    uint32_t dst = xb_s + (uint32_t)lane * 16u;
+    if (!(ha.y & (CHF_PARTIAL_X << 16)))
     {
-        const int t = t0 + lane;
-        const bool full = t < ntiles && (int)(tilecol[t] * TS + TS) <= colA;
-        nfull += __popc(__ballot_sync(0xffffffffu, full));
-    }
-    if (lane == 0)
-        mbar_expect_tx(xbar, nfull * SEG);
-    __syncwarp();
+        // xpiece = x + (lane % PPT) * EPP: one 64-bit multiply-add per copy
 #pragma unroll 1
-    for (int t = lane; t < ntiles; t += 32)
-    {
-        const int col0 = (int)(tilecol[t] * TS);
-        if (col0 + TS <= colA)
-            tma_load_1d(xb_s + (uint32_t)t * SEG, x + col0, SEG, xbar);
-        else
+        for (int t0 = 0; t0 < ntiles; t0 += 2 * TPI)
         {
-#pragma unroll 1
-            for (int c = 0; c < TS; c++)
-                xb[t * TS + c] = col0 + c < colA ? x[col0 + c] : (T)0;
+            const int t = t0 + lane / PPT;
+            const bool p0 = t < ntiles, p1 = t + TPI < ntiles;
+            uint32_t c0 = 0, c1 = 0;
+            if (p0)
+                c0 = lds_u32(tilecol_s + 4u * (uint32_t)t0);
+            if (p1)
+                c1 = lds_u32(tilecol_s + 4u * (uint32_t)(t0 + TPI));
+            if (p0)
+                cp_async_16(dst, xpiece + (size_t)c0 * TS);
+            if (p1)
+                cp_async_16(dst + 512u, xpiece + (size_t)c1 * TS);
+            dst += 1024u;
         }
     }
-    const uint32_t xs_s = xb_s + (uint32_t)ntiles * SEG;
-#pragma unroll 1
-    for (int e = lane; e < nside; e += 32)
+    else
     {
-        const T *src = x + sidecol[e];
+        const int piece = lane % PPT;
+#pragma unroll 1
+        for (int t = lane / PPT; t < ntiles; t += TPI, dst += 512u)
+        {
+            const int col0 = (int)lds_u32(tilecol_s + 4u * (uint32_t)(t - lane / PPT)) * TS + piece * EPP;
+            int valid = colA - col0;
+            valid = valid < 0 ? 0 : (valid > EPP ? EPP : valid);
+            cp_async_16_zfill(dst, valid ? x + col0 : x, (uint32_t)valid * (uint32_t)sizeof(T));
+        }
+    }
+    uint32_t dst2 = xb_s + (uint32_t)ntiles * (uint32_t)(TS * sizeof(T)) + (uint32_t)lane * (uint32_t)sizeof(T);
+#pragma unroll 1
+    for (int e = lane; e < nside; e += 32, dst2 += 32u * (uint32_t)sizeof(T))
+    {
+        const T *src = x + lds_u32(sidecol_s + 4u * (uint32_t)(e - lane));
         if (sizeof(T) == 8)
-            cp_async_8(xs_s + (uint32_t)e * 8u, src);
+            cp_async_8(dst2, src);
         else
-            cp_async_4(xs_s + (uint32_t)e * 4u, src);
+            cp_async_4(dst2, src);
     }
 }
 
@@ -192,48 +270,82 @@ struct Vec2<float>
 // with one 128-bit shared-memory load per lane.
 // ---------------------------------------------------------------------------------------------
 template <class T>
-__device__ __forceinline__ void process_chunk(const unsigned char *st, const T *xb, const SpmvArgs<T> &a, int lane)
+__device__ __forceinline__ void process_chunk(const unsigned char *st, uint32_t st_s, const T *xb, uint32_t xb_s,
+                                              uint32_t zero_s, const SpmvArgs<T> &a, int lane)
 {
     typedef typename Vec2<T>::type V2;
-    const ChunkHeader h = *reinterpret_cast<const ChunkHeader *>(st);
-    const uint4 *rows = reinterpret_cast<const uint4 *>(st + CHUNK_OFF_ROWS);
-    const uint2 *odesc = reinterpret_cast<const uint2 *>(st + h.off_odesc);
-    const unsigned char *sidehdr = st + h.off_sidehdr;
-    const T *sideval = reinterpret_cast<const T *>(st + h.off_sideval);
-    const unsigned char *pay = st + h.off_payload;
-    const T *xside = xb + (int)h.ntiles * TS;
+    constexpr uint32_t VS = (uint32_t)sizeof(T);
+    const uint4 ha = lds_v4(st_s);
+    const int nrows = (int)(ha.x & 0xffffu), ntiles = (int)(ha.x >> 16);
     const int p = lane & 7, g = lane >> 3;
-    const int nrows = (int)h.nrows;
+    const uint2 *odesc = reinterpret_cast<const uint2 *>(st + (ha.z >> 16));
+    uint32_t sidehdr_s = st_s + (ha.w & 0xffffu) + 4u * (uint32_t)p;
+    uint32_t sideval_s = st_s + (ha.w >> 16);                    // values of the extracted nonzeros ...
+    uint32_t xside_s = xb_s + (uint32_t)ntiles * (TS * VS);      // ... and their staged x operands
+    uint32_t pay_s = st_s + lds_u32(st_s + 16u);
+    uint32_t rows_s = st_s + CHUNK_OFF_ROWS;
 
-    for (int rr = 0; rr < nrows; rr++)
+#pragma unroll 1
+    for (int rr = 0; rr < nrows; rr++, rows_s += 16u)
     {
-        const uint4 rec = rows[rr];
+        const uint4 rec = lds_v4(rows_s);
         const int nsr = (int)(rec.y & 0xffffu);
         const int nother = (int)(rec.y >> 16);
-        const int rowlen = (int)(rec.z & 0xffu);
-        const unsigned flags = (rec.z >> 8) & 0xffu;
+        const bool has_side = (rec.z & (ROWF_HAS_SIDE << 8)) != 0;
+        uint32_t w0 = 0, w1 = 0, wt = 0;
+        if (has_side) // issued early: independent of the ELL loop
+        {
+            w0 = lds_u32(sidehdr_s);
+            w1 = lds_u32(sidehdr_s + 4u);
+            wt = lds_u32(sidehdr_s + 32u - 4u * (uint32_t)p);
+        }
         T a0 = 0, a1 = 0;
 
-        // ---- ELL group: one flat loop over the slot-rows of all ELL tiles of the row ----
+        // ---- ELL group: one flat loop over the slot-rows of all ELL tiles of the row, 4 slot-rows
+        //      per lane and trip, every load of a trip in flight at once (predicated tail).
+        //      Padding slots hold value 0 / column 0 and are multiplied through like in the
+        //      reference GPU kernel (tilespmv_cuda.h:597-598); only tilespmv_cpu.h:182 skips them
         {
-            const V2 *vals = reinterpret_cast<const V2 *>(pay);
-            const unsigned char *idx = pay + nsr * TS * (int)sizeof(T);
-            const unsigned char *xsel = idx + nsr * 8;
-#pragma unroll 2
-            for (int sr = g; sr < nsr; sr += 4)
+            uint32_t va = pay_s + (uint32_t)lane * (2u * VS);                  // V2 of (slot-row g, pair p)
+            uint32_t ia = pay_s + (uint32_t)nsr * (TS * VS) + (uint32_t)lane;   // its nibble byte
+            uint32_t sa = pay_s + (uint32_t)nsr * (TS * VS + 8u) + (uint32_t)g; // its x-segment selector
+            int left = nsr;
+#pragma unroll 1
+            for (; left >= 16; left -= 16) // 16 slot-rows: every lane has 4, no predicates
             {
-                const V2 v = vals[sr * 8 + p];
-                const unsigned b = idx[sr * 8 + p];
-                const T *xs = xb + (int)xsel[sr] * TS;
-                // padding slots hold value 0 / column 0 and are multiplied through like in the
-                // reference GPU kernel (tilespmv_cuda.h:597-598); only tilespmv_cpu.h:182 skips them
-                a0 = fma_t<T>(v.x, xs[b >> 4], a0);
-                a1 = fma_t<T>(v.y, xs[b & 15u], a1);
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                {
+                    const V2 v = SL<T>::ld2(va + (uint32_t)j * (64u * VS));
+                    const uint32_t b = lds_u8(ia + 32u * (uint32_t)j);
+                    const uint32_t xo = xb_s + lds_u8(sa + 4u * (uint32_t)j) * (TS * VS);
+                    a0 = fma_t<T>(v.x, SL<T>::ld(mad_u32(b >> 4, VS, xo)), a0);
+                    a1 = fma_t<T>(v.y, SL<T>::ld(mad_u32(b & 15u, VS, xo)), a1);
+                }
+                va += 256u * VS;
+                ia += 128u;
+                sa += 16u;
             }
-            pay += nsr * TS * (int)sizeof(T) + (int)pad16((uint32_t)nsr * 9u);
+            if (left > 0) // tail: slot-rows past the end read the CTA's zero block instead (branch-free)
+            {
+                const int rem = left - g; // this lane's slot-rows: 4*j < rem
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                {
+                    const bool ok = 4 * j < rem;
+                    const V2 v = SL<T>::ld2(ok ? va + (uint32_t)j * (64u * VS) : zero_s);
+                    const uint32_t b = lds_u8(ia + 32u * (uint32_t)j);
+                    const uint32_t xo = xb_s + lds_u8(sa + 4u * (uint32_t)j) * (TS * VS);
+                    a0 = fma_t<T>(v.x, SL<T>::ld(ok ? mad_u32(b >> 4, VS, xo) : zero_s), a0);
+                    a1 = fma_t<T>(v.y, SL<T>::ld(ok ? mad_u32(b & 15u, VS, xo) : zero_s), a1);
+                }
+            }
+            pay_s += (rec.w & 0xffffu) * 16u;
         }
+        const unsigned char *pay = st + (pay_s - st_s);
 
         // ---- the other tiles of the row ----
+#pragma unroll 1
         for (int t = 0; t < nother; t++)
         {
             const uint2 d = *odesc++;
@@ -325,50 +437,53 @@ __device__ __forceinline__ void process_chunk(const unsigned char *st, const T *
             }
         }
 
-        // ---- extracted very-sparse nonzeros of this block row: 4 lanes per row pair ----
-        if (flags & ROWF_HAS_SIDE)
+        // ---- extracted very-sparse nonzeros of this block row: 4 lanes per row pair, one
+        //      predicated loop with a warp-uniform trip count, 4 trips' loads in flight at once ----
+        pay_s = st_s + (uint32_t)(pay - st);
+        if (has_side)
         {
-            const uint16_t *sh = reinterpret_cast<const uint16_t *>(sidehdr);
-            sidehdr += SIDEHDR_BYTES;
-            const int s0 = sh[2 * p], s1 = sh[2 * p + 1], e1 = sh[2 * p + 2];
+            const uint32_t s1 = w0 >> 16, e1 = w1 & 0xffffu;
+            uint32_t k0 = (w0 & 0xffffu) + (uint32_t)g, k1 = s1 + (uint32_t)g;
+            const int nit = (int)(rec.z >> 16);
 #pragma unroll 1
-            for (int e = s0 + g; e < s1; e += 4)
-                a0 = fma_t<T>(sideval[e], xside[e], a0);
-#pragma unroll 1
-            for (int e = s1 + g; e < e1; e += 4)
-                a1 = fma_t<T>(sideval[e], xside[e], a1);
-            const int total = sh[16];
-            sideval += total;
-            xside += total;
+            for (int i = 0; i < nit; i += 2)
+            {
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+                {
+                    const uint32_t o0 = k0 + 4u * j < s1 ? (k0 + 4u * j) * VS : ~0u;
+                    const uint32_t o1 = k1 + 4u * j < e1 ? (k1 + 4u * j) * VS : ~0u;
+                    a0 = fma_t<T>(SL<T>::ld(o0 != ~0u ? sideval_s + o0 : zero_s), SL<T>::ld(o0 != ~0u ? xside_s + o0 : zero_s), a0);
+                    a1 = fma_t<T>(SL<T>::ld(o1 != ~0u ? sideval_s + o1 : zero_s), SL<T>::ld(o1 != ~0u ? xside_s + o1 : zero_s), a1);
+                }
+                k0 += 8u;
+                k1 += 8u;
+            }
+            const uint32_t total = wt & 0xffffu;
+            sideval_s += total * VS;
+            xside_s += total * VS;
+            sidehdr_s += SIDEHDR_BYTES;
         }
 
-        // ---- combine the 4 lane groups, lanes 0..7 store rows (2p, 2p+1) with one 16-byte store ----
-        a0 += __shfl_xor_sync(0xffffffffu, a0, 8);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, 8);
-        a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
-        if (lane < 8 && 2 * lane < rowlen)
+        // ---- combine the 4 lane groups: after the exchange lanes with even g hold row 2p, lanes
+        //      with odd g hold row 2p+1; lanes 0..15 write the 16 y values as one 128-byte store ----
         {
-            const bool partial = (rec.x & ROW_PARTIAL) != 0;
-            const size_t row = (size_t)(rec.x & ~ROW_PARTIAL) * TS + 2 * lane;
-            T *dst = (partial ? a.scratch : a.y) + row;
-            if (2 * lane + 1 < rowlen)
+            const bool odd = (g & 1) != 0;
+            const T send = odd ? a0 : a1;
+            T acc = odd ? a1 : a0;
+            acc += __shfl_xor_sync(0xffffffffu, send, 8);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            const int rowlen = (int)(rec.z & 0xffu);
+            const int r = 2 * p + (g & 1);
+            if (lane < 16 && r < rowlen)
             {
-                V2 o;
-                o.x = a0;
-                o.y = a1;
-                *reinterpret_cast<V2 *>(dst) = o;
+                const bool partial = (rec.x & ROW_PARTIAL) != 0;
+                const size_t row = (size_t)(rec.x & ~ROW_PARTIAL) * TS + r;
+                (partial ? a.scratch : a.y)[row] = acc;
+                if (!partial)
+                    for (int q = 0; q < a.npeers; q++) // fused all-gather: next x of every peer
+                        a.peers[q][a.row_offset + (long long)row] = acc;
             }
-            else
-                dst[0] = a0;
-            if (!partial)
-                for (int q = 0; q < a.npeers; q++) // fused all-gather: next x of every peer
-                {
-                    T *px = a.peers[q] + a.row_offset + (long long)row;
-                    px[0] = a0;
-                    if (2 * lane + 1 < rowlen)
-                        px[1] = a1;
-                }
         }
     }
 }
@@ -382,84 +497,90 @@ __global__ void __launch_bounds__(SPMV_MAX_WARPS * 32, 1) tile_spmv_kernel(const
     const uint32_t per_warp = (uint32_t)(SPMV_STAGES * a.chunk_bytes + 2 * a.xstage_bytes);
     unsigned char *wbase = smem + SPMV_BAR_BYTES + (size_t)warp * per_warp;
     unsigned char *xbase = wbase + (size_t)SPMV_STAGES * a.chunk_bytes;
-    // per warp: SPMV_STAGES barriers for the chunk stream + 2 for the staged x segments
+    // per warp: SPMV_STAGES barriers for the chunk stream
     const uint32_t bar0 = smem_u32(smem) + (uint32_t)(warp * SPMV_BARS_PER_WARP * 8);
-    const uint32_t xbar0 = bar0 + 8u * SPMV_MAX_STAGES;
 
     // warp w of CTA b takes chunks gw, gw + nw, ...: neighbouring warps stream neighbouring chunks
-    const long long gw = (long long)blockIdx.x * nwarps_cta + warp;
-    const long long nw = (long long)gridDim.x * nwarps_cta;
+    const unsigned gw = blockIdx.x * nwarps_cta + warp;
+    const unsigned nw = gridDim.x * nwarps_cta;
     const int nk = gw < a.nchunks ? (int)((a.nchunks - gw + nw - 1) / nw) : 0;
+    // 64 bytes of zeros behind the barriers: where predicated-off loads of the tail loops land
+    const uint32_t zero_s = smem_u32(smem) + (uint32_t)(SPMV_BAR_BYTES - 64);
+    if (threadIdx.x < 16)
+        reinterpret_cast<uint32_t *>(smem + SPMV_BAR_BYTES - 64)[threadIdx.x] = 0u;
+    __syncthreads();
     if (nk == 0)
         return;
 
     if (lane == 0)
     {
 #pragma unroll
-        for (int i = 0; i < SPMV_BARS_PER_WARP; i++)
+        for (int i = 0; i < SPMV_STAGES; i++)
             mbar_init(bar0 + 8u * i, 1);
         fence_mbar_init();
     }
     __syncwarp();
 
     const uint32_t stage0 = smem_u32(wbase);
-    auto issue = [&](int k, unsigned long long off, unsigned long long end) { // lane 0 only
+    auto issue = [&](int k, uint2 d) { // lane 0 only: d = {offset / 16, bytes}
         const int st = k % SPMV_STAGES;
-        const uint32_t bytes = (uint32_t)(end - off);
-        mbar_expect_tx(bar0 + 8u * st, bytes);
-        tma_load_1d(stage0 + (uint32_t)st * (uint32_t)a.chunk_bytes, a.stream + off, bytes, bar0 + 8u * st);
+        mbar_expect_tx(bar0 + 8u * st, d.y);
+        tma_load_1d(stage0 + (uint32_t)st * (uint32_t)a.chunk_bytes, a.stream + (size_t)d.x * 16u, d.y, bar0 + 8u * st);
     };
-    // lane 0 keeps the offsets of the NEXT chunk to issue in registers, loaded one iteration early
-    unsigned long long nxt_off = 0, nxt_end = 0;
+    // lane 0 keeps the descriptor of the NEXT chunk to issue in registers, loaded one iteration early
+    uint2 nxt = make_uint2(0u, 0u);
     if (lane == 0)
     {
         for (int k = 0; k < SPMV_STAGES && k < nk; k++)
-        {
-            const long long c = gw + (long long)k * nw;
-            issue(k, a.chunk_off[c], a.chunk_off[c + 1]);
-        }
+            issue(k, a.chunk_desc[gw + (unsigned)k * nw]);
         if (SPMV_STAGES < nk)
-        {
-            const long long c = gw + (long long)SPMV_STAGES * nw;
-            nxt_off = a.chunk_off[c];
-            nxt_end = a.chunk_off[c + 1];
-        }
+            nxt = a.chunk_desc[gw + (unsigned)SPMV_STAGES * nw];
     }
 
+    // per-lane source of the x pieces: x + (lane % pieces-per-segment) * elements-per-piece
+    const T *xpiece = a.x + (lane % (TS * (int)sizeof(T) / 16)) * (16 / (int)sizeof(T));
+    const uint32_t xb0 = smem_u32(xbase);
+    const uint32_t cb = (uint32_t)a.chunk_bytes, xsb = (uint32_t)a.xstage_bytes;
+
     mbar_wait(bar0, 0);
-    stage_x<T>(wbase, reinterpret_cast<T *>(xbase), xbar0, a.x, a.colA, lane);
+    stage_x<T>(stage0, xb0, a.x, xpiece, a.colA, lane);
     cp_async_commit();
 
+    // st / ph: stage and mbarrier phase of chunk k;  st1 / ph1: of chunk k+1
+    uint32_t st = 0, ph = 0;
 #pragma unroll 1
     for (int k = 0; k < nk; k++)
     {
-        const int st = k % SPMV_STAGES;
+        uint32_t st1 = st + 1, ph1 = ph;
+        if (st1 == SPMV_STAGES)
+        {
+            st1 = 0;
+            ph1 ^= 1u;
+        }
+        const uint32_t xcur = xb0 + (uint32_t)(k & 1) * xsb;
         if (k + 1 < nk)
         {
-            const int st1 = (k + 1) % SPMV_STAGES;
-            mbar_wait(bar0 + 8u * st1, (uint32_t)(((k + 1) / SPMV_STAGES) & 1));
-            stage_x<T>(wbase + (size_t)st1 * a.chunk_bytes,
-                       reinterpret_cast<T *>(xbase + (size_t)((k + 1) & 1) * a.xstage_bytes), xbar0 + 8u * ((k + 1) & 1),
-                       a.x, a.colA, lane);
+            mbar_wait(bar0 + 8u * st1, ph1);
+            stage_x<T>(stage0 + st1 * cb, xb0 + (uint32_t)((k + 1) & 1) * xsb, a.x, xpiece, a.colA, lane);
         }
         cp_async_commit();
-        cp_async_wait<1>();                                          // gathers of chunk k (this thread's) ...
-        mbar_wait(xbar0 + 8u * (k & 1), (uint32_t)((k >> 1) & 1));  // ... its x segments ...
-        __syncwarp();                                                // ... and everybody else's copies
-        process_chunk<T>(wbase + (size_t)st * a.chunk_bytes,
-                         reinterpret_cast<const T *>(xbase + (size_t)(k & 1) * a.xstage_bytes), a, lane);
+        cp_async_wait<1>(); // this lane's x copies of chunk k have landed ...
+        __syncwarp();       // ... and so have everybody else's
+        process_chunk<T>(wbase + (size_t)st * cb, stage0 + st * cb,
+                         reinterpret_cast<const T *>(xbase + (size_t)(k & 1) * xsb), xcur, zero_s, a, lane);
         __syncwarp(); // all lanes are done reading stage st and x buffer k&1
         if (lane == 0 && k + SPMV_STAGES < nk)
         {
-            fence_proxy_async();
-            issue(k + SPMV_STAGES, nxt_off, nxt_end);
+            // the reads above were consumed by the arithmetic before the y store was issued, so
+            // the stage can be handed back to the async proxy (same hand-over as a consumer
+            // release -> producer TMA in a warp-specialised pipeline)
+            mbar_expect_tx(bar0 + 8u * st, nxt.y);
+            tma_load_1d(stage0 + st * cb, a.stream + (size_t)nxt.x * 16u, nxt.y, bar0 + 8u * st);
             if (k + SPMV_STAGES + 1 < nk)
-            {
-                const long long c = gw + (long long)(k + SPMV_STAGES + 1) * nw;
-                nxt_off = a.chunk_off[c];
-                nxt_end = a.chunk_off[c + 1];
-            }
+                nxt = a.chunk_desc[gw + (unsigned)(k + SPMV_STAGES + 1) * nw];
         }
+        st = st1;
+        ph = ph1;
     }
     cp_async_wait<0>();
 }
@@ -553,8 +674,8 @@ static int plan_launch_t(tilespmv_plan *P, const T *x, T *y, cudaStream_t s)
         return TILESPMV_OK;
     SpmvArgs<T> a;
     a.stream = P->stream.as<unsigned char>();
-    a.chunk_off = P->chunk_off.as<unsigned long long>();
-    a.nchunks = P->nchunks;
+    a.chunk_desc = P->chunk_desc.as<uint2>();
+    a.nchunks = (unsigned)P->nchunks;
     a.x = x;
     a.y = y;
     a.scratch = P->scratch.as<T>();

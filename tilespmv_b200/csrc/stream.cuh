@@ -7,11 +7,11 @@
 //
 //   ChunkHeader                          32 B
 //   RowRec   [nrows]                     16 B each  block rows (or pieces of long block rows)
-//   TileCol  [ntiles] u32                pad 8      tile column of every stream tile (x staging)
-//   ODesc    [nother]                     8 B each  descriptors of the non-ELL tiles
-//   SideHdr  [#rows with side][20] u16   40 B each  17 exclusive row starts of the extracted nnz
-//   SideCol  [nside] u32                 pad 8      GLOBAL columns of the extracted nonzeros
-//   SideVal  [nside] T                   pad 8
+//   TileCol  [ntiles] u32                pad 16     tile column of every stream tile (x staging)
+//   SideCol  [nside] u32                 pad 16     GLOBAL columns of the extracted nonzeros (x staging)
+//   ODesc    [nother]                     8 B each  descriptors of the non-ELL tiles, pad 16
+//   SideHdr  [#rows with side][20] u16   40 B each  17 exclusive row starts of the extracted nnz, pad 16
+//   SideVal  [nside] T                   pad 16
 //   payload, row after row:
 //     ELL group of the row -- ALL slot-rows (16 values, one per local row) of its ELL/HYB tiles,
 //     flattened so the kernel runs one branch-free loop over them:
@@ -21,7 +21,7 @@
 //         Dense    : val[16][16] T column-major (rows / columns padded with zeros)
 //         DenseRow : val[ndr][16] T row-major (padded); row ids as a 16-bit mask in the descriptor
 //         DenseCol : val[ndc][16] T slot-major | 16 column nibbles in one u64
-//   pad to 16
+// The two staging lists come first so that the x fetch of a chunk can start from its first bytes.
 // Nibble parity is TILE-LOCAL here (element e sits in byte e/2, high nibble when e is even); the
 // reference's global-position parity (csr2tile.h:973, :982) only exists in Tile_matrix.
 // COO tiles are not in the stream as tiles: their nonzeros live in the side part exactly once
@@ -32,30 +32,34 @@
 namespace tsp
 {
 
-struct ChunkHeader // 32 B
+struct ChunkHeader // 32 B, read by the kernel as two 128-bit shared-memory loads
 {
     uint16_t nrows;
-    uint16_t ntiles; // stream tiles (ELL + other), = number of staged x segments
-    uint32_t nside;
-    uint32_t nother;
-    uint32_t off_odesc;
-    uint32_t off_sidehdr;
-    uint32_t off_sidecol;
-    uint32_t off_sideval;
+    uint16_t ntiles;      // stream tiles (ELL + other), = number of staged x segments (<= 256)
+    uint16_t nside;
+    uint16_t flags;       // CHF_*
+    uint16_t off_sidecol; // byte offsets from the start of the chunk (chunks are <= 32 KB)
+    uint16_t off_odesc;
+    uint16_t off_sidehdr;
+    uint16_t off_sideval;
     uint32_t off_payload;
+    uint32_t nother;
+    uint32_t pad[2];
 };
 static_assert(sizeof(ChunkHeader) == 32, "ChunkHeader must be 32 bytes");
+constexpr uint32_t CHF_PARTIAL_X = 1u; // some x segment sticks out past colA (zero-filled staging path)
 constexpr uint32_t CHUNK_OFF_ROWS = 32;
 
-struct RowRec // 16 B
+struct RowRec // 16 B, one 128-bit shared-memory load
 {
-    uint32_t dest;   // block row index, or ROW_PARTIAL | partial-sum slot for a piece of a split row
-    uint16_t nsr;    // slot-rows in the row's ELL group
-    uint16_t nother; // non-ELL tiles
-    uint8_t rowlen;  // rows that exist (16 except in the last block row)
-    uint8_t flags;   // ROWF_*
+    uint32_t dest;       // block row index, or ROW_PARTIAL | partial-sum slot for a piece of a split row
+    uint16_t nsr;        // slot-rows in the row's ELL group
+    uint16_t nother;     // non-ELL tiles
+    uint8_t rowlen;      // rows that exist (16 except in the last block row)
+    uint8_t flags;       // ROWF_*
+    uint16_t side_nit;   // trip count of the side loop: max over local rows of ceil(#entries / 4)
+    uint16_t ell_bytes16; // bytes of the ELL group / 16
     uint16_t pad0;
-    uint32_t pad1;
 };
 static_assert(sizeof(RowRec) == 16, "RowRec must be 16 bytes");
 constexpr uint32_t ROW_PARTIAL = 0x80000000u;
@@ -98,8 +102,8 @@ __host__ __device__ inline uint32_t ell_group_bytes(uint32_t nsr, uint32_t vs)
 __host__ __device__ inline uint32_t chunk_layout_bytes(uint32_t nrows, uint32_t ntiles, uint32_t nother,
                                                        uint32_t nsiderows, uint32_t nside, uint32_t payload, uint32_t vs)
 {
-    return pad16(CHUNK_OFF_ROWS + 16u * nrows + pad8(4u * ntiles) + 8u * nother + SIDEHDR_BYTES * nsiderows +
-                 pad8(4u * nside) + pad8(vs * nside)) + payload; // payload parts are multiples of 16
+    return CHUNK_OFF_ROWS + 16u * nrows + pad16(4u * ntiles) + pad16(4u * nside) + pad16(8u * nother) +
+           pad16(SIDEHDR_BYTES * nsiderows) + pad16(vs * nside) + payload; // payload parts are multiples of 16
 }
 
 // one schedulable unit: a whole block row, or a piece of a long one
