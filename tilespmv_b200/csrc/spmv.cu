@@ -131,6 +131,13 @@ __device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
     return r;
 }
+// p + a * b as one 64-bit multiply-add (global address of a tile's x segment / a side column)
+__device__ __forceinline__ const void *mad_wide(uint32_t a, uint32_t b, const void *p)
+{
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(reinterpret_cast<unsigned long long>(p)));
+    return reinterpret_cast<const void *>(r);
+}
 template <class T>
 struct SL;
 template <>
@@ -220,9 +227,9 @@ __device__ __forceinline__ void stage_x(uint32_t st_s, uint32_t xb_s, const T *_
             if (p1)
                 c1 = lds_u32(tilecol_s + 4u * (uint32_t)(t0 + TPI));
             if (p0)
-                cp_async_16(dst, xpiece + (size_t)c0 * TS);
+                cp_async_16(dst, mad_wide(c0, TS * (uint32_t)sizeof(T), xpiece));
             if (p1)
-                cp_async_16(dst + 512u, xpiece + (size_t)c1 * TS);
+                cp_async_16(dst + 512u, mad_wide(c1, TS * (uint32_t)sizeof(T), xpiece));
             dst += 1024u;
         }
     }
@@ -242,7 +249,7 @@ __device__ __forceinline__ void stage_x(uint32_t st_s, uint32_t xb_s, const T *_
 #pragma unroll 1
     for (int e = lane; e < nside; e += 32, dst2 += 32u * (uint32_t)sizeof(T))
     {
-        const T *src = x + lds_u32(sidecol_s + 4u * (uint32_t)(e - lane));
+        const void *src = mad_wide(lds_u32(sidecol_s + 4u * (uint32_t)(e - lane)), (uint32_t)sizeof(T), x);
         if (sizeof(T) == 8)
             cp_async_8(dst2, src);
         else
@@ -280,8 +287,8 @@ __device__ __forceinline__ void process_chunk(const unsigned char *st, uint32_t 
     const int p = lane & 7, g = lane >> 3;
     const uint2 *odesc = reinterpret_cast<const uint2 *>(st + (ha.z >> 16));
     uint32_t sidehdr_s = st_s + (ha.w & 0xffffu) + 4u * (uint32_t)p;
-    uint32_t sideval_s = st_s + (ha.w >> 16);                    // values of the extracted nonzeros ...
-    uint32_t xside_s = xb_s + (uint32_t)ntiles * (TS * VS);      // ... and their staged x operands
+    const T *sideval = reinterpret_cast<const T *>(st + (ha.w >> 16)); // values of the extracted nonzeros ...
+    const T *xside = xb + ntiles * TS;                                  // ... and their staged x operands
     uint32_t pay_s = st_s + lds_u32(st_s + 16u);
     uint32_t rows_s = st_s + CHUNK_OFF_ROWS;
 
@@ -310,35 +317,49 @@ __device__ __forceinline__ void process_chunk(const unsigned char *st, uint32_t 
             uint32_t ia = pay_s + (uint32_t)nsr * (TS * VS) + (uint32_t)lane;   // its nibble byte
             uint32_t sa = pay_s + (uint32_t)nsr * (TS * VS + 8u) + (uint32_t)g; // its x-segment selector
             int left = nsr;
+            auto slot = [&](uint32_t j) { // slot-row g + 4*j of the current position, unpredicated
+                const V2 v = SL<T>::ld2(va + j * (64u * VS));
+                const uint32_t b = lds_u8(ia + 32u * j);
+                const uint32_t xo = xb_s + lds_u8(sa + 4u * j) * (TS * VS);
+                a0 = fma_t<T>(v.x, SL<T>::ld(mad_u32(b >> 4, VS, xo)), a0);
+                a1 = fma_t<T>(v.y, SL<T>::ld(mad_u32(b & 15u, VS, xo)), a1);
+            };
+            auto slot_if = [&](uint32_t j, bool ok) { // predicated-off lanes read the CTA's zero block
+                const V2 v = SL<T>::ld2(ok ? va + j * (64u * VS) : zero_s);
+                const uint32_t b = lds_u8(ia + 32u * j);
+                const uint32_t xo = xb_s + lds_u8(sa + 4u * j) * (TS * VS);
+                a0 = fma_t<T>(v.x, SL<T>::ld(ok ? mad_u32(b >> 4, VS, xo) : zero_s), a0);
+                a1 = fma_t<T>(v.y, SL<T>::ld(ok ? mad_u32(b & 15u, VS, xo) : zero_s), a1);
+            };
 #pragma unroll 1
-            for (; left >= 16; left -= 16) // 16 slot-rows: every lane has 4, no predicates
+            for (; left >= 16; left -= 16) // 16 slot-rows: every lane has 4, all loads of the trip in flight
             {
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                {
-                    const V2 v = SL<T>::ld2(va + (uint32_t)j * (64u * VS));
-                    const uint32_t b = lds_u8(ia + 32u * (uint32_t)j);
-                    const uint32_t xo = xb_s + lds_u8(sa + 4u * (uint32_t)j) * (TS * VS);
-                    a0 = fma_t<T>(v.x, SL<T>::ld(mad_u32(b >> 4, VS, xo)), a0);
-                    a1 = fma_t<T>(v.y, SL<T>::ld(mad_u32(b & 15u, VS, xo)), a1);
-                }
+                slot(0);
+                slot(1);
+                slot(2);
+                slot(3);
                 va += 256u * VS;
                 ia += 128u;
                 sa += 16u;
             }
-            if (left > 0) // tail: slot-rows past the end read the CTA's zero block instead (branch-free)
+            if (left >= 8)
             {
-                const int rem = left - g; // this lane's slot-rows: 4*j < rem
-#pragma unroll
-                for (int j = 0; j < 4; j++)
+                slot(0);
+                slot(1);
+                va += 128u * VS;
+                ia += 64u;
+                sa += 8u;
+                left -= 8;
+            }
+            if (left > 0) // 1..7 slot-rows left
+            {
+                if (left > 4)
                 {
-                    const bool ok = 4 * j < rem;
-                    const V2 v = SL<T>::ld2(ok ? va + (uint32_t)j * (64u * VS) : zero_s);
-                    const uint32_t b = lds_u8(ia + 32u * (uint32_t)j);
-                    const uint32_t xo = xb_s + lds_u8(sa + 4u * (uint32_t)j) * (TS * VS);
-                    a0 = fma_t<T>(v.x, SL<T>::ld(ok ? mad_u32(b >> 4, VS, xo) : zero_s), a0);
-                    a1 = fma_t<T>(v.y, SL<T>::ld(ok ? mad_u32(b & 15u, VS, xo) : zero_s), a1);
+                    slot(0);
+                    slot_if(1, g + 4 < left);
                 }
+                else
+                    slot_if(0, g < left);
             }
             pay_s += (rec.w & 0xffffu) * 16u;
         }
@@ -446,22 +467,22 @@ __device__ __forceinline__ void process_chunk(const unsigned char *st, uint32_t 
             uint32_t k0 = (w0 & 0xffffu) + (uint32_t)g, k1 = s1 + (uint32_t)g;
             const int nit = (int)(rec.z >> 16);
 #pragma unroll 1
-            for (int i = 0; i < nit; i += 2)
+            for (int i = 0; i < nit; i += 2) // trips past a lane's last entry are predicated off
             {
-#pragma unroll
-                for (int j = 0; j < 2; j++)
-                {
-                    const uint32_t o0 = k0 + 4u * j < s1 ? (k0 + 4u * j) * VS : ~0u;
-                    const uint32_t o1 = k1 + 4u * j < e1 ? (k1 + 4u * j) * VS : ~0u;
-                    a0 = fma_t<T>(SL<T>::ld(o0 != ~0u ? sideval_s + o0 : zero_s), SL<T>::ld(o0 != ~0u ? xside_s + o0 : zero_s), a0);
-                    a1 = fma_t<T>(SL<T>::ld(o1 != ~0u ? sideval_s + o1 : zero_s), SL<T>::ld(o1 != ~0u ? xside_s + o1 : zero_s), a1);
-                }
+                if (k0 < s1)
+                    a0 = fma_t<T>(sideval[k0], xside[k0], a0);
+                if (k1 < e1)
+                    a1 = fma_t<T>(sideval[k1], xside[k1], a1);
+                if (k0 + 4u < s1)
+                    a0 = fma_t<T>(sideval[k0 + 4u], xside[k0 + 4u], a0);
+                if (k1 + 4u < e1)
+                    a1 = fma_t<T>(sideval[k1 + 4u], xside[k1 + 4u], a1);
                 k0 += 8u;
                 k1 += 8u;
             }
             const uint32_t total = wt & 0xffffu;
-            sideval_s += total * VS;
-            xside_s += total * VS;
+            sideval += total;
+            xside += total;
             sidehdr_s += SIDEHDR_BYTES;
         }
 
