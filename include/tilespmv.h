@@ -230,8 +230,9 @@ typedef struct
     int chunk_bytes;  /* max bytes of one scheduler chunk of the packed stream (0 = default) */
     int xstage_bytes; /* max bytes of x staged in shared memory per chunk (0 = default)      */
     int ctas_per_sm;  /* persistent CTAs per SM (0 = default: 1, with as many warps as fit)  */
-    int stages;       /* TMA pipeline depth per warp, 2..4 (0 = default)                     */
-    int reserved[4];
+    int stages;       /* TMA pipeline depth per warp, 2..4 (0 = default: 2)                  */
+    int max_warps;    /* cap on warps per CTA (0 = as many as shared memory holds, <= 20)    */
+    int reserved[3];
 } tilespmv_plan_options;
 
 /* Packs the tiles into the 16-byte-aligned per-chunk stream and builds the persistent,

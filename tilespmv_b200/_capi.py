@@ -61,7 +61,7 @@ class DmatInfo(C.Structure):
 
 class PlanOptions(C.Structure):
     _fields_ = [("chunk_bytes", C.c_int), ("xstage_bytes", C.c_int), ("ctas_per_sm", C.c_int),
-                ("stages", C.c_int), ("reserved", C.c_int * 4)]
+                ("stages", C.c_int), ("max_warps", C.c_int), ("reserved", C.c_int * 3)]
 
 
 class PlanInfo(C.Structure):

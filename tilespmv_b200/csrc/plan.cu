@@ -100,6 +100,10 @@ struct PackArgs
     const unsigned long long *chunk_off;
     TileScans sc;
     unsigned char *stream;
+    unsigned char *head; // lists of every warp's first chunk, head_stride bytes apart
+    long long nw;        // lookahead distance = warps of the persistent grid
+    int stages;          // TMA pipeline depth the stream is laid out for
+    int head_stride;
     int *error_flag;
     // Tile_matrix (device)
     int rowA, colA, tilem, tilen;
@@ -233,18 +237,65 @@ __device__ void pack_other_tile(const PackArgs<T> &a, int t, int br, unsigned xs
 
 constexpr int PACK_ITEM_INTS = 6; // per item: tile base, other base, payload base, side base, sidehdr idx, nsr
 
+// x-staging lists of chunk cn (tile column of every stream tile, global column of every extracted
+// nonzero, in the order the chunk's xsel / side indices use); runs on the whole CTA.  Returns this
+// thread's share of the CHF_* flags.
+template <class T>
+__device__ unsigned write_lists(const PackArgs<T> &a, long long cn, uint32_t *tilecol, uint32_t *sidecol)
+{
+    const long long j0 = a.chunk_item0[cn], j1 = a.chunk_item0[cn + 1];
+    const bool ragged_cols = (a.colA % TS) != 0;
+    unsigned flags = 0;
+    int tbase = 0, sbase = 0;
+    for (long long j = j0; j < j1; j++)
+    {
+        const PlanItem it = a.items[j];
+        const int nc0 = a.sc.nc[it.t0];
+        for (int t = it.t0 + (int)threadIdx.x; t < it.t1; t += (int)blockDim.x)
+        {
+            if (a.Format[t] == TILESPMV_FMT_COO)
+                continue;
+            const int tc = a.tile_columnidx[t];
+            tilecol[tbase + (a.sc.nc[t] - nc0)] = (uint32_t)tc;
+            if (ragged_cols && tc == a.tilen - 1)
+                flags |= CHF_PARTIAL_X;
+        }
+        tbase += a.sc.nc[it.t1] - nc0;
+        const int ns = it.s1 - it.s0;
+        for (int e = (int)threadIdx.x; e < ns; e += (int)blockDim.x)
+            sidecol[sbase + e] = (uint32_t)a.side_col[it.s0 + e];
+        sbase += ns;
+    }
+    return flags;
+}
+
+// counts of a chunk's lists (serial, one thread)
+template <class T>
+__device__ void list_counts(const PackArgs<T> &a, long long cn, uint32_t &nt, uint32_t &ns)
+{
+    nt = ns = 0;
+    for (long long j = a.chunk_item0[cn]; j < a.chunk_item0[cn + 1]; j++)
+    {
+        const PlanItem it = a.items[j];
+        nt += (uint32_t)(a.sc.nc[it.t1] - a.sc.nc[it.t0]);
+        ns += (uint32_t)(it.s1 - it.s0);
+    }
+}
+
 template <class T>
 __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long long nchunks)
 {
     extern __shared__ int s_base[];
     __shared__ ChunkHeader hdr;
     __shared__ int s_start[TS + 1];
-    __shared__ unsigned s_flags;
+    __shared__ unsigned s_flags, s_head_flags;
+    __shared__ uint32_t s_own_nt, s_own_ns;
     const long long c = blockIdx.x;
     if (c >= nchunks)
         return;
     const long long i0 = a.chunk_item0[c], i1 = a.chunk_item0[c + 1];
     const int nitems = (int)(i1 - i0);
+    const long long cn = c + a.nw; // the chunk whose lists this one carries
     unsigned char *out = a.stream + a.chunk_off[c];
     constexpr uint32_t vs = (uint32_t)sizeof(T);
 
@@ -282,30 +333,40 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long 
             nside += (uint32_t)ns;
             nsiderows += ns > 0 ? 1u : 0u;
         }
+        uint32_t next_nt = 0, next_ns = 0;
+        if (cn < nchunks)
+            list_counts<T>(a, cn, next_nt, next_ns);
         hdr.nrows = (uint16_t)nitems;
         hdr.ntiles = (uint16_t)ntiles;
-        hdr.nside = (uint16_t)nside;
-        hdr.flags = 0;
-        const uint32_t off_sidecol = CHUNK_OFF_ROWS + 16u * (uint32_t)nitems + pad16(4u * ntiles);
-        const uint32_t off_odesc = off_sidecol + pad16(4u * nside);
+        hdr.next_ntiles = (uint16_t)next_nt;
+        hdr.next_nside = (uint16_t)next_ns;
+        const uint32_t off_odesc = CHUNK_OFF_ROWS + 16u * (uint32_t)nitems;
         const uint32_t off_sidehdr = off_odesc + pad16(8u * nother);
         const uint32_t off_sideval = off_sidehdr + pad16(SIDEHDR_BYTES * nsiderows);
-        hdr.off_sidecol = (uint16_t)off_sidecol;
+        const uint32_t off_payload = off_sideval + pad16(vs * nside);
+        const uint32_t off_nextlist = off_payload + pay;
+        hdr.off_nextlist = (uint16_t)off_nextlist;
         hdr.off_odesc = (uint16_t)off_odesc;
         hdr.off_sidehdr = (uint16_t)off_sidehdr;
         hdr.off_sideval = (uint16_t)off_sideval;
-        hdr.off_payload = off_sideval + pad16(vs * nside);
-        hdr.nother = nother;
-        hdr.pad[0] = hdr.pad[1] = 0;
+        hdr.off_payload = off_payload;
+        hdr.next_flags = 0;
+        hdr.nside = (uint16_t)nside;
+        {
+            const long long ci = c + (long long)a.stages * a.nw; // fetched into this chunk's stage once it is consumed
+            hdr.issue_off16 = ci < nchunks ? (uint32_t)(a.chunk_off[ci] / 16) : 0u;
+            hdr.issue_bytes = ci < nchunks ? (uint32_t)(a.chunk_off[ci + 1] - a.chunk_off[ci]) : 0u;
+        }
         *reinterpret_cast<ChunkHeader *>(out) = hdr;
-        if ((unsigned long long)(hdr.off_payload + pay) != a.chunk_off[c + 1] - a.chunk_off[c] || ntiles > 256u ||
-            nside > 0xffffu || hdr.off_payload > 0xffffu)
+        if ((unsigned long long)(off_nextlist + list_bytes(next_nt, next_ns)) != a.chunk_off[c + 1] - a.chunk_off[c] ||
+            ntiles > 256u || nside > 0xffffu || off_nextlist > 0xffffu)
             atomicExch(a.error_flag, 1);
         s_flags = 0;
+        s_head_flags = 0;
+        s_own_nt = ntiles;
+        s_own_ns = nside;
     }
     __syncthreads();
-    uint32_t *tilecol = reinterpret_cast<uint32_t *>(out + CHUNK_OFF_ROWS + 16 * nitems);
-    const bool ragged_cols = (a.colA % TS) != 0;
 
     for (int k = 0; k < nitems; k++)
     {
@@ -324,10 +385,6 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long 
             if (f == TILESPMV_FMT_COO)
                 continue;
             const unsigned xsel = (unsigned)(sb[0] + (a.sc.nc[t] - a.sc.nc[it.t0])); // x segment in the chunk
-            const int tc = a.tile_columnidx[t];
-            tilecol[xsel] = (uint32_t)tc;
-            if (ragged_cols && tc == a.tilen - 1)
-                atomicOr(&s_flags, CHF_PARTIAL_X);
             if (fmt_is_ell(f))
             {
                 const uint32_t so = (uint32_t)(a.sc.ws[t] - a.sc.ws[it.t0]);
@@ -358,13 +415,9 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long 
                 s_start[r] = st;
                 reinterpret_cast<uint16_t *>(out + hdr.off_sidehdr + SIDEHDR_BYTES * (uint32_t)sb[4])[r] = (uint16_t)st;
             }
-            uint32_t *oc = reinterpret_cast<uint32_t *>(out + hdr.off_sidecol) + sb[3];
             T *ov = reinterpret_cast<T *>(out + hdr.off_sideval) + sb[3];
             for (int e = threadIdx.x; e < ns; e += PACK_THREADS)
-            {
-                oc[e] = (uint32_t)a.side_col[it.s0 + e];
                 ov[e] = a.side_val[it.s0 + e];
-            }
             __syncthreads();
             if (threadIdx.x == 0)
             {
@@ -379,9 +432,37 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long 
             __syncthreads();
         }
     }
+
+    // lists of the chunk the same warp processes next
+    if (cn < nchunks)
+    {
+        uint32_t *tl = reinterpret_cast<uint32_t *>(out + hdr.off_nextlist);
+        const unsigned f = write_lists<T>(a, cn, tl, tl + pad16(4u * hdr.next_ntiles) / 4u);
+        if (f)
+            atomicOr(&s_flags, f);
+    }
+    // every warp's first chunk: its own lists go to the head array
+    if (c < a.nw)
+    {
+        unsigned char *h = a.head + (size_t)c * a.head_stride;
+        uint32_t *tl = reinterpret_cast<uint32_t *>(h + HEAD_HDR_BYTES);
+        const unsigned f = write_lists<T>(a, c, tl, tl + pad16(4u * s_own_nt) / 4u);
+        if (f)
+            atomicOr(&s_head_flags, f);
+    }
     __syncthreads();
-    if (threadIdx.x == 0 && s_flags)
-        reinterpret_cast<ChunkHeader *>(out)->flags = (uint16_t)s_flags;
+    if (threadIdx.x == 0)
+    {
+        if (s_flags)
+            reinterpret_cast<ChunkHeader *>(out)->next_flags = (uint16_t)s_flags;
+        if (c < a.nw)
+        {
+            uint32_t *h = reinterpret_cast<uint32_t *>(a.head + (size_t)c * a.head_stride);
+            h[0] = s_own_nt | (s_own_ns << 16);
+            h[1] = s_head_flags;
+            h[2] = h[3] = 0;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -393,7 +474,10 @@ struct ChunkAcc
 {
     uint32_t nrows = 0, ntiles = 0, nother = 0, nsiderows = 0, nside = 0, payload = 0;
     bool empty() const { return nrows == 0; }
-    uint32_t bytes(uint32_t vs) const { return chunk_layout_bytes(nrows, ntiles, nother, nsiderows, nside, payload, vs); }
+    uint32_t main_bytes(uint32_t vs) const { return chunk_main_bytes(nrows, nother, nsiderows, nside, payload, vs); }
+    // budget check: the chunk with lists as long as its own (the lists it really carries are those
+    // of the chunk the same warp processes next; the stage stride is widened afterwards if needed)
+    uint32_t bytes(uint32_t vs) const { return main_bytes(vs) + list_bytes(ntiles, nside); }
     uint32_t xbytes(uint32_t vs) const { return ntiles * 16u * vs + nside * vs; }
     void add(const ChunkAcc &o)
     {
@@ -466,18 +550,18 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
     std::vector<unsigned long long> chunk_off;
     std::vector<int> split_tab; // 4 ints per split row
     items.reserve((size_t)tilem + 16);
-    unsigned long long off = 0;
     int64_t nslots = 0;
     ChunkAcc acc;
+    std::vector<uint32_t> ch_main, ch_nt, ch_ns; // per chunk: bytes without lists, stream tiles, side entries
     auto close_chunk = [&]() {
         if (acc.empty())
             return;
-        off += acc.bytes(vs);
-        chunk_off.push_back(off);
+        ch_main.push_back(acc.main_bytes(vs));
+        ch_nt.push_back(acc.ntiles);
+        ch_ns.push_back(acc.nside);
         chunk_item0.push_back((long long)items.size());
         acc = ChunkAcc();
     };
-    chunk_off.push_back(0);
     chunk_item0.push_back(0);
     std::vector<long long> h_ob;
     std::vector<int> h_nc, h_oc, h_ws;
@@ -603,11 +687,73 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
         }
     }
     close_chunk();
-    const long long nchunks = (long long)chunk_off.size() - 1;
+    const long long nchunks = (long long)ch_main.size();
+    if (nchunks > 0x7fffffffll)
+    {
+        set_error("plan: too many chunks");
+        return TILESPMV_ERR_UNSUPPORTED;
+    }
     P->nchunks = nchunks;
-    P->stream_bytes = (int64_t)off;
     P->nsplit = (int64_t)split_tab.size() / 4;
     P->nslots = nslots;
+
+    // ---- 2b. launch shape and the lookahead distance nw.  Chunk c carries the x-staging lists of
+    //          chunk c + nw (what the same warp processes next), so its size -- and with it the
+    //          stage stride, the warps that fit and nw itself -- depend on each other: iterate to
+    //          the fixed point (uniform matrices converge at once), else fall back to the
+    //          nw-independent bound max(main) + max(list).
+    uint32_t max_main = 0, max_list = 0, max_x = 0;
+    for (long long c = 0; c < nchunks; c++)
+    {
+        max_x = std::max(max_x, ch_nt[(size_t)c] * 16u * vs + ch_ns[(size_t)c] * vs);
+        max_main = std::max(max_main, ch_main[(size_t)c]);
+        max_list = std::max(max_list, list_bytes(ch_nt[(size_t)c], ch_ns[(size_t)c]));
+    }
+    auto stride_for_nw = [&](long long nw) {
+        uint32_t need = 0;
+        for (long long c = 0; c < nchunks; c++)
+        {
+            const long long n = c + nw;
+            const uint32_t lb = n < nchunks ? list_bytes(ch_nt[(size_t)n], ch_ns[(size_t)n]) : 0u;
+            need = std::max(need, ch_main[(size_t)c] + lb);
+        }
+        return (int)((need + 127u) & ~127u);
+    };
+    P->xstage_bytes = std::max(128, (int)((max_x + 127u) & ~127u)); // what the chunks really need (<= the X budget)
+    P->stage_stride = std::max(128, (int)((std::max(max_main, std::min((uint32_t)C, max_main + max_list)) + 127u) & ~127u));
+    bool converged = false;
+    for (int it = 0; it < 6 && !converged; it++)
+    {
+        TSP_TRY(spmv_configure(P));
+        const int need = nchunks ? stride_for_nw(P->nw) : 128;
+        if (need <= P->stage_stride)
+            converged = true;
+        else
+            P->stage_stride = need;
+    }
+    if (!converged)
+    {
+        P->stage_stride = (int)((max_main + max_list + 127u) & ~127u);
+        TSP_TRY(spmv_configure(P));
+    }
+    const long long nw = P->nw;
+    chunk_off.resize((size_t)nchunks + 1);
+    chunk_off[0] = 0;
+    for (long long c = 0; c < nchunks; c++)
+    {
+        const long long n = c + nw;
+        const uint32_t lb = n < nchunks ? list_bytes(ch_nt[(size_t)n], ch_ns[(size_t)n]) : 0u;
+        chunk_off[(size_t)c + 1] = chunk_off[(size_t)c] + ch_main[(size_t)c] + lb;
+    }
+    const unsigned long long off = chunk_off[(size_t)nchunks];
+    P->stream_bytes = (int64_t)off;
+    // lists of every warp's first chunk
+    const long long nhead = std::min(nw, nchunks);
+    uint32_t head_list = 0;
+    for (long long c = 0; c < nhead; c++)
+        head_list = std::max(head_list, list_bytes(ch_nt[(size_t)c], ch_ns[(size_t)c]));
+    P->head_stride = (int)(HEAD_HDR_BYTES + head_list);
+    TSP_TRY(P->head.alloc((size_t)std::max<long long>(nhead, 1) * (size_t)P->head_stride, true, s));
 
     // ---- 3. upload tables, pack ----
     DevBuf d_items, d_chunk_item0, d_err;
@@ -648,6 +794,10 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
         a.chunk_off = P->chunk_off.as<unsigned long long>();
         a.sc = sc;
         a.stream = P->stream.as<unsigned char>();
+        a.head = P->head.as<unsigned char>();
+        a.nw = P->nw;
+        a.stages = P->stages;
+        a.head_stride = P->head_stride;
         a.error_flag = d_err.as<int>();
         a.rowA = dm->rowA;
         a.colA = dm->colA;
@@ -722,6 +872,7 @@ int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tiles
     P->xstage_bytes = opts && opts->xstage_bytes ? opts->xstage_bytes : (vs == 8 ? 2048 : 1024);
     P->ctas_per_sm = opts ? opts->ctas_per_sm : 0;
     P->stages = opts ? opts->stages : 0;
+    P->max_warps = opts ? opts->max_warps : 0;
     if (P->chunk_bytes < 2560 || P->chunk_bytes > 32768 || (P->chunk_bytes & 127) || P->xstage_bytes < 16 * vs ||
         P->xstage_bytes > 32768 || (P->xstage_bytes & 127))
     {
@@ -729,7 +880,6 @@ int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tiles
                   16 * vs);
         return TILESPMV_ERR_INVALID;
     }
-    TSP_TRY(spmv_configure(P));
     if (vs == 8)
         TSP_TRY(plan_build_t<double>(dm, P, s));
     else

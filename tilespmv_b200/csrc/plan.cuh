@@ -18,6 +18,10 @@ struct tilespmv_plan
     tsp::DevBuf stream;    // the packed bytes
     tsp::DevBuf chunk_off; // uint64[nchunks+1], 16-byte aligned offsets into stream (planner / packer)
     tsp::DevBuf chunk_desc; // uint2[nchunks+1] {offset / 16, bytes}: what the kernel's TMA issue reads
+    tsp::DevBuf head;       // x-staging lists of every warp's first chunk (stream.cuh), head_stride apart
+    int head_stride = 0;
+    int stage_stride = 0;   // bytes of one TMA stage in shared memory (>= the largest chunk)
+    long long nw = 0;       // warps of the persistent grid = lookahead distance of the lists
 
     // block rows that were cut across chunks: partial sums land in scratch and are combined by the
     // fix-up kernel in a fixed order (deterministic, no atomics)
@@ -26,7 +30,7 @@ struct tilespmv_plan
     tsp::DevBuf split_tab; // int4 {block row, first slot, #slots, rowlen} per split row
 
     // launch configuration of the persistent kernel
-    int grid = 0, block = 0, smem = 0, ctas_per_sm = 0, sm_count = 0, stages = 0;
+    int grid = 0, block = 0, smem = 0, ctas_per_sm = 0, sm_count = 0, stages = 0, max_warps = 0;
 
     // roofline accounting
     int64_t b_alg = 0, b_csr = 0;
@@ -41,7 +45,7 @@ struct tilespmv_plan
 
     int64_t device_bytes() const
     {
-        return (int64_t)(stream.bytes + chunk_off.bytes + chunk_desc.bytes + scratch.bytes + split_tab.bytes + hx.bytes + hy.bytes);
+        return (int64_t)(stream.bytes + chunk_off.bytes + chunk_desc.bytes + head.bytes + scratch.bytes + split_tab.bytes + hx.bytes + hy.bytes);
     }
 };
 

@@ -28,7 +28,13 @@
 namespace tsp
 {
 
-constexpr int SPMV_MAX_WARPS = 16;
+constexpr int SPMV_MAX_WARPS = 24; // sizes the barrier area
+// warps per CTA by pipeline depth: what 227 KB of shared memory hold with 4 KB stages, and the
+// register budget that goes with it (65536 / threads): 20 warps -> 96 registers (register files are handed out 4 warps at a time), 16 -> 128
+__host__ __device__ constexpr int spmv_max_warps(int stages) { return stages == 2 ? 21 : (stages == 3 ? 16 : 12); }
+// the 2-stage kernel exists in two register budgets: 80 (up to 21 warps; register files are handed
+// out 4 warps at a time, so 21 warps count as 24) and 96 (up to 20 warps)
+constexpr int SPMV_REGS_LO = 80, SPMV_REGS_HI = 96;
 constexpr int SPMV_MAX_STAGES = 4;
 constexpr int SPMV_BARS_PER_WARP = SPMV_MAX_STAGES;                // one mbarrier per chunk stage
 constexpr int SPMV_BAR_BYTES = SPMV_MAX_WARPS * SPMV_BARS_PER_WARP * 8 + 256; // padded to 128 B
@@ -185,7 +191,9 @@ struct SpmvArgs
     T *y;
     T *scratch;
     int colA;
-    int chunk_bytes, xstage_bytes;
+    const unsigned char *head; // x-staging lists of every warp's first chunk
+    int head_stride;
+    int stage_stride, xstage_bytes;
     int npeers;
     long long row_offset;
     T *peers[TSP_MAX_PEERS];
@@ -200,20 +208,27 @@ struct SpmvArgs
 // of 16) is zero-filled through the src-size operand (chunks flagged CHF_PARTIAL_X only).
 // Completion is tracked by the cp.async group of the calling iteration (no mbarrier).
 // ---------------------------------------------------------------------------------------------
-template <class T>
-__device__ __forceinline__ void stage_x(uint32_t st_s, uint32_t xb_s, const T *__restrict__ x, const T *__restrict__ xpiece,
-                                        int colA, int lane)
+// list access: shared memory (lists carried by the previous chunk) or global (head array)
+template <bool GLOBAL>
+__device__ __forceinline__ uint32_t list_u32(uint32_t s_addr, const uint32_t *g_ptr, uint32_t byte_off)
+{
+    if (GLOBAL)
+        return __ldg(g_ptr + byte_off / 4u);
+    return lds_u32(s_addr + byte_off);
+}
+
+template <class T, bool GLOBAL>
+__device__ __forceinline__ void stage_x(uint32_t list_s, const uint32_t *list_g, int ntiles, int nside, unsigned flags,
+                                        uint32_t xb_s, const T *__restrict__ x, const T *__restrict__ xpiece, int colA,
+                                        int lane)
 {
     constexpr int PPT = TS * (int)sizeof(T) / 16; // 16-byte pieces per segment
     constexpr int TPI = 32 / PPT;                 // segments per warp instruction
     constexpr int EPP = 16 / (int)sizeof(T);      // elements per piece
-    const uint4 ha = lds_v4(st_s);
-    const int nrows = (int)(ha.x & 0xffffu), ntiles = (int)(ha.x >> 16);
-    const int nside = (int)(ha.y & 0xffffu);
-    const uint32_t tilecol_s = st_s + CHUNK_OFF_ROWS + 16u * (uint32_t)nrows + 4u * (uint32_t)(lane / PPT);
-    const uint32_t sidecol_s = st_s + (ha.z & 0xffffu) + 4u * (uint32_t)lane;
+    const uint32_t tl = 4u * (uint32_t)(lane / PPT);                                      // this lane's tile column ...
+    const uint32_t sl = ((4u * (uint32_t)ntiles + 15u) & ~15u) + 4u * (uint32_t)lane;     // ... and side column
     uint32_t dst = xb_s + (uint32_t)lane * 16u;
-    if (!(ha.y & (CHF_PARTIAL_X << 16)))
+    if (!(flags & CHF_PARTIAL_X))
     {
         // xpiece = x + (lane % PPT) * EPP: one 64-bit multiply-add per copy
 #pragma unroll 1
@@ -223,9 +238,9 @@ __device__ __forceinline__ void stage_x(uint32_t st_s, uint32_t xb_s, const T *_
             const bool p0 = t < ntiles, p1 = t + TPI < ntiles;
             uint32_t c0 = 0, c1 = 0;
             if (p0)
-                c0 = lds_u32(tilecol_s + 4u * (uint32_t)t0);
+                c0 = list_u32<GLOBAL>(list_s, list_g, tl + 4u * (uint32_t)t0);
             if (p1)
-                c1 = lds_u32(tilecol_s + 4u * (uint32_t)(t0 + TPI));
+                c1 = list_u32<GLOBAL>(list_s, list_g, tl + 4u * (uint32_t)(t0 + TPI));
             if (p0)
                 cp_async_16(dst, mad_wide(c0, TS * (uint32_t)sizeof(T), xpiece));
             if (p1)
@@ -239,7 +254,7 @@ __device__ __forceinline__ void stage_x(uint32_t st_s, uint32_t xb_s, const T *_
 #pragma unroll 1
         for (int t = lane / PPT; t < ntiles; t += TPI, dst += 512u)
         {
-            const int col0 = (int)lds_u32(tilecol_s + 4u * (uint32_t)(t - lane / PPT)) * TS + piece * EPP;
+            const int col0 = (int)list_u32<GLOBAL>(list_s, list_g, 4u * (uint32_t)t) * TS + piece * EPP;
             int valid = colA - col0;
             valid = valid < 0 ? 0 : (valid > EPP ? EPP : valid);
             cp_async_16_zfill(dst, valid ? x + col0 : x, (uint32_t)valid * (uint32_t)sizeof(T));
@@ -249,7 +264,7 @@ __device__ __forceinline__ void stage_x(uint32_t st_s, uint32_t xb_s, const T *_
 #pragma unroll 1
     for (int e = lane; e < nside; e += 32, dst2 += 32u * (uint32_t)sizeof(T))
     {
-        const void *src = mad_wide(lds_u32(sidecol_s + 4u * (uint32_t)(e - lane)), (uint32_t)sizeof(T), x);
+        const void *src = mad_wide(list_u32<GLOBAL>(list_s, list_g, sl + 4u * (uint32_t)(e - lane)), (uint32_t)sizeof(T), x);
         if (sizeof(T) == 8)
             cp_async_8(dst2, src);
         else
@@ -509,15 +524,16 @@ __device__ __forceinline__ void process_chunk(const unsigned char *st, uint32_t 
     }
 }
 
-template <class T, int SPMV_STAGES>
-__global__ void __launch_bounds__(SPMV_MAX_WARPS * 32, 1) tile_spmv_kernel(const SpmvArgs<T> a)
+template <class T, int SPMV_STAGES, int MAXREG>
+__global__ void __maxnreg__(MAXREG) tile_spmv_kernel(const SpmvArgs<T> a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps_cta = blockDim.x >> 5;
-    const uint32_t per_warp = (uint32_t)(SPMV_STAGES * a.chunk_bytes + 2 * a.xstage_bytes);
+    const uint32_t cb = (uint32_t)a.stage_stride, xsb = (uint32_t)a.xstage_bytes;
+    const uint32_t per_warp = SPMV_STAGES * cb + 2u * xsb;
     unsigned char *wbase = smem + SPMV_BAR_BYTES + (size_t)warp * per_warp;
-    unsigned char *xbase = wbase + (size_t)SPMV_STAGES * a.chunk_bytes;
+    unsigned char *xbase = wbase + (size_t)SPMV_STAGES * cb;
     // per warp: SPMV_STAGES barriers for the chunk stream
     const uint32_t bar0 = smem_u32(smem) + (uint32_t)(warp * SPMV_BARS_PER_WARP * 8);
 
@@ -543,65 +559,65 @@ __global__ void __launch_bounds__(SPMV_MAX_WARPS * 32, 1) tile_spmv_kernel(const
     __syncwarp();
 
     const uint32_t stage0 = smem_u32(wbase);
-    auto issue = [&](int k, uint2 d) { // lane 0 only: d = {offset / 16, bytes}
-        const int st = k % SPMV_STAGES;
-        mbar_expect_tx(bar0 + 8u * st, d.y);
-        tma_load_1d(stage0 + (uint32_t)st * (uint32_t)a.chunk_bytes, a.stream + (size_t)d.x * 16u, d.y, bar0 + 8u * st);
-    };
-    // lane 0 keeps the descriptor of the NEXT chunk to issue in registers, loaded one iteration early
-    uint2 nxt = make_uint2(0u, 0u);
+    // the first SPMV_STAGES chunks are fetched from the descriptor table; every later fetch takes
+    // its descriptor from the header of the chunk whose stage it re-uses (no global load in the loop)
     if (lane == 0)
     {
         for (int k = 0; k < SPMV_STAGES && k < nk; k++)
-            issue(k, a.chunk_desc[gw + (unsigned)k * nw]);
-        if (SPMV_STAGES < nk)
-            nxt = a.chunk_desc[gw + (unsigned)SPMV_STAGES * nw];
+        {
+            const uint2 d = a.chunk_desc[gw + (unsigned)k * nw];
+            mbar_expect_tx(bar0 + 8u * k, d.y);
+            tma_load_1d(stage0 + (uint32_t)k * cb, a.stream + (size_t)d.x * 16u, d.y, bar0 + 8u * k);
+        }
     }
 
     // per-lane source of the x pieces: x + (lane % pieces-per-segment) * elements-per-piece
     const T *xpiece = a.x + (lane % (TS * (int)sizeof(T) / 16)) * (16 / (int)sizeof(T));
     const uint32_t xb0 = smem_u32(xbase);
-    const uint32_t cb = (uint32_t)a.chunk_bytes, xsb = (uint32_t)a.xstage_bytes;
 
-    mbar_wait(bar0, 0);
-    stage_x<T>(stage0, xb0, a.x, xpiece, a.colA, lane);
-    cp_async_commit();
+    // x operand of the warp's first chunk: its lists come from the head array
+    {
+        const uint32_t *h = reinterpret_cast<const uint32_t *>(a.head + (size_t)gw * (size_t)a.head_stride);
+        const uint32_t cnt = __ldg(h), fl = __ldg(h + 1);
+        stage_x<T, true>(0u, h + HEAD_HDR_BYTES / 4, (int)(cnt & 0xffffu), (int)(cnt >> 16), fl, xb0, a.x, xpiece, a.colA, lane);
+        cp_async_commit();
+    }
 
-    // st / ph: stage and mbarrier phase of chunk k;  st1 / ph1: of chunk k+1
+    // st / ph: stage and mbarrier phase of chunk k
     uint32_t st = 0, ph = 0;
 #pragma unroll 1
     for (int k = 0; k < nk; k++)
     {
-        uint32_t st1 = st + 1, ph1 = ph;
-        if (st1 == SPMV_STAGES)
-        {
-            st1 = 0;
-            ph1 ^= 1u;
-        }
+        const uint32_t st_s = stage0 + st * cb;
         const uint32_t xcur = xb0 + (uint32_t)(k & 1) * xsb;
-        if (k + 1 < nk)
+        mbar_wait(bar0 + 8u * st, ph);
+        const uint2 issue = make_uint2(lds_u32(st_s + 24u), lds_u32(st_s + 28u)); // what to fetch into this stage next
+        if (k + 1 < nk) // stage the x operand of chunk k+1 from the lists chunk k carries
         {
-            mbar_wait(bar0 + 8u * st1, ph1);
-            stage_x<T>(stage0 + st1 * cb, xb0 + (uint32_t)((k + 1) & 1) * xsb, a.x, xpiece, a.colA, lane);
+            const uint4 ha = lds_v4(st_s);
+            const uint32_t fl = lds_u32(st_s + 20u);
+            stage_x<T, false>(st_s + (ha.z & 0xffffu), nullptr, (int)(ha.y & 0xffffu), (int)(ha.y >> 16), fl & 0xffffu,
+                              xb0 + (uint32_t)((k + 1) & 1) * xsb, a.x, xpiece, a.colA, lane);
         }
         cp_async_commit();
         cp_async_wait<1>(); // this lane's x copies of chunk k have landed ...
         __syncwarp();       // ... and so have everybody else's
-        process_chunk<T>(wbase + (size_t)st * cb, stage0 + st * cb,
-                         reinterpret_cast<const T *>(xbase + (size_t)(k & 1) * xsb), xcur, zero_s, a, lane);
+        process_chunk<T>(wbase + (size_t)st * cb, st_s, reinterpret_cast<const T *>(xbase + (size_t)(k & 1) * xsb), xcur,
+                         zero_s, a, lane);
         __syncwarp(); // all lanes are done reading stage st and x buffer k&1
-        if (lane == 0 && k + SPMV_STAGES < nk)
+        if (lane == 0 && issue.y != 0u)
         {
             // the reads above were consumed by the arithmetic before the y store was issued, so
             // the stage can be handed back to the async proxy (same hand-over as a consumer
             // release -> producer TMA in a warp-specialised pipeline)
-            mbar_expect_tx(bar0 + 8u * st, nxt.y);
-            tma_load_1d(stage0 + st * cb, a.stream + (size_t)nxt.x * 16u, nxt.y, bar0 + 8u * st);
-            if (k + SPMV_STAGES + 1 < nk)
-                nxt = a.chunk_desc[gw + (unsigned)(k + SPMV_STAGES + 1) * nw];
+            mbar_expect_tx(bar0 + 8u * st, issue.y);
+            tma_load_1d(st_s, a.stream + (size_t)issue.x * 16u, issue.y, bar0 + 8u * st);
         }
-        st = st1;
-        ph = ph1;
+        if (++st == SPMV_STAGES)
+        {
+            st = 0;
+            ph ^= 1u;
+        }
     }
     cp_async_wait<0>();
 }
@@ -634,22 +650,34 @@ __global__ void __launch_bounds__(128)
 // ---------------------------------------------------------------------------------------------
 static size_t warp_smem_bytes(const tilespmv_plan *P)
 {
-    return (size_t)P->stages * P->chunk_bytes + 2 * (size_t)P->xstage_bytes;
+    return (size_t)P->stages * P->stage_stride + 2 * (size_t)P->xstage_bytes;
 }
 
 template <class T>
-static int set_kernel_attrs(int stages, int smem)
+static const void *kernel_for(int stages, int warps)
 {
-    const void *fn = stages == 2   ? (const void *)tile_spmv_kernel<T, 2>
-                     : stages == 3 ? (const void *)tile_spmv_kernel<T, 3>
-                                   : (const void *)tile_spmv_kernel<T, 4>;
-    TSP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (stages == 2)
+        return warps > 20 ? (const void *)tile_spmv_kernel<T, 2, SPMV_REGS_LO> : (const void *)tile_spmv_kernel<T, 2, SPMV_REGS_HI>;
+    if (stages == 3)
+        return (const void *)tile_spmv_kernel<T, 3, 128>;
+    return (const void *)tile_spmv_kernel<T, 4, 128>;
+}
+
+template <class T>
+static int set_kernel_attrs(int stages, int warps, int smem_optin)
+{
+    // the attribute is per kernel, not per plan: always raise it to the device limit so that plans
+    // with different shared-memory footprints can coexist in one process
+    const void *fn = kernel_for<T>(stages, warps);
+    TSP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
     TSP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     return TILESPMV_OK;
 }
 
 // One persistent CTA per SM (ctas_per_sm can raise it); the CTA gets as many independent warps as
-// its shared memory holds -- every warp owns SPMV_STAGES chunk buffers + 2 x-staging buffers.
+// its shared memory holds -- every warp owns `stages` chunk buffers of stage_stride bytes + 2
+// x-staging buffers.  Needs P->nchunks and P->stage_stride; sets grid / block / smem and the
+// lookahead distance nw = grid * warps that the packer bakes into the stream.
 int spmv_configure(tilespmv_plan *P)
 {
     int dev = 0;
@@ -660,7 +688,7 @@ int spmv_configure(tilespmv_plan *P)
     if (P->ctas_per_sm <= 0)
         P->ctas_per_sm = 1;
     if (P->stages < 2 || P->stages > SPMV_MAX_STAGES)
-        P->stages = 4;
+        P->stages = 2;
     if (P->ctas_per_sm > 8)
         P->ctas_per_sm = 8;
     const size_t budget = ((size_t)smem_optin + 1024) / P->ctas_per_sm - 1024; // 1 KB per CTA is reserved
@@ -672,19 +700,30 @@ int spmv_configure(tilespmv_plan *P)
         return TILESPMV_ERR_INVALID;
     }
     int warps = (int)((budget - SPMV_BAR_BYTES) / per_warp);
-    if (warps > SPMV_MAX_WARPS / P->ctas_per_sm)
-        warps = SPMV_MAX_WARPS / P->ctas_per_sm;
+    // default for 2 stages: 20 warps on the 96-register kernel (measured faster than 21 on 80)
+    int cap = spmv_max_warps(P->stages);
+    if (P->stages == 2 && P->max_warps <= 0)
+        cap = 20;
+    if (P->max_warps > 0 && cap > P->max_warps)
+        cap = P->max_warps;
+    if (warps > cap / P->ctas_per_sm)
+        warps = cap / P->ctas_per_sm;
     if (warps < 1)
         warps = 1;
     const size_t smem = SPMV_BAR_BYTES + (size_t)warps * per_warp;
+    int grid = sms * P->ctas_per_sm;
+    const long long ctas_needed = (P->nchunks + warps - 1) / warps;
+    if (ctas_needed < grid)
+        grid = (int)(ctas_needed > 0 ? ctas_needed : 1);
     P->sm_count = sms;
-    P->grid = sms * P->ctas_per_sm;
+    P->grid = grid;
     P->block = warps * 32;
     P->smem = (int)smem;
+    P->nw = (long long)grid * warps;
     if (P->precision == 8)
-        TSP_TRY(set_kernel_attrs<double>(P->stages, (int)smem));
+        TSP_TRY(set_kernel_attrs<double>(P->stages, warps, smem_optin));
     else
-        TSP_TRY(set_kernel_attrs<float>(P->stages, (int)smem));
+        TSP_TRY(set_kernel_attrs<float>(P->stages, warps, smem_optin));
     return TILESPMV_OK;
 }
 
@@ -701,23 +740,25 @@ static int plan_launch_t(tilespmv_plan *P, const T *x, T *y, cudaStream_t s)
     a.y = y;
     a.scratch = P->scratch.as<T>();
     a.colA = P->colA;
-    a.chunk_bytes = P->chunk_bytes;
+    a.head = P->head.as<unsigned char>();
+    a.head_stride = P->head_stride;
+    a.stage_stride = P->stage_stride;
     a.xstage_bytes = P->xstage_bytes;
     a.npeers = P->npeers;
     a.row_offset = P->row_offset;
     for (int p = 0; p < TSP_MAX_PEERS; p++)
         a.peers[p] = reinterpret_cast<T *>(P->peers[p]);
-    const int warps = P->block / 32;
-    int grid = P->grid;
-    const long long ctas_needed = (P->nchunks + warps - 1) / warps;
-    if (ctas_needed < grid)
-        grid = (int)ctas_needed;
-    if (P->stages == 2)
-        TSP_LAUNCH((tile_spmv_kernel<T, 2>), grid, P->block, (size_t)P->smem, s, a);
-    else if (P->stages == 3)
-        TSP_LAUNCH((tile_spmv_kernel<T, 3>), grid, P->block, (size_t)P->smem, s, a);
-    else
-        TSP_LAUNCH((tile_spmv_kernel<T, 4>), grid, P->block, (size_t)P->smem, s, a);
+    const int grid = P->grid; // fixed at plan time: the stream's lookahead lists depend on it
+    {
+        void *args[] = {(void *)&a};
+        cudaError_t err = cudaLaunchKernel(kernel_for<T>(P->stages, P->block / 32), dim3(grid), dim3(P->block), args, (size_t)P->smem, s);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (err != cudaSuccess)
+        {
+            set_error("launch of tile_spmv_kernel failed: %s", cudaGetErrorString(err));
+            return TILESPMV_ERR_CUDA;
+        }
+    }
     if (P->nsplit > 0)
     {
         const long long threads = P->nsplit * TS;

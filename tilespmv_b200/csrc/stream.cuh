@@ -7,8 +7,6 @@
 //
 //   ChunkHeader                          32 B
 //   RowRec   [nrows]                     16 B each  block rows (or pieces of long block rows)
-//   TileCol  [ntiles] u32                pad 16     tile column of every stream tile (x staging)
-//   SideCol  [nside] u32                 pad 16     GLOBAL columns of the extracted nonzeros (x staging)
 //   ODesc    [nother]                     8 B each  descriptors of the non-ELL tiles, pad 16
 //   SideHdr  [#rows with side][20] u16   40 B each  17 exclusive row starts of the extracted nnz, pad 16
 //   SideVal  [nside] T                   pad 16
@@ -21,7 +19,12 @@
 //         Dense    : val[16][16] T column-major (rows / columns padded with zeros)
 //         DenseRow : val[ndr][16] T row-major (padded); row ids as a 16-bit mask in the descriptor
 //         DenseCol : val[ndc][16] T slot-major | 16 column nibbles in one u64
-// The two staging lists come first so that the x fetch of a chunk can start from its first bytes.
+//   x-staging lists of the chunk the SAME WARP processes next (chunk index + nw, nw = warps of the
+//   persistent grid): TileCol [next ntiles] u32 pad 16 | SideCol [next nside] u32 pad 16
+//     = tile column of every stream tile / GLOBAL column of every extracted nonzero of that chunk.
+//     Carrying them one chunk early lets the warp stage the x operand of chunk k+1 while it works
+//     on chunk k without chunk k+1 having arrived, so two TMA stages per warp suffice.  The lists
+//     of each warp's first chunk live in a small separate array (plan.head).
 // Nibble parity is TILE-LOCAL here (element e sits in byte e/2, high nibble when e is even); the
 // reference's global-position parity (csr2tile.h:973, :982) only exists in Tile_matrix.
 // COO tiles are not in the stream as tiles: their nonzeros live in the side part exactly once
@@ -35,16 +38,18 @@ namespace tsp
 struct ChunkHeader // 32 B, read by the kernel as two 128-bit shared-memory loads
 {
     uint16_t nrows;
-    uint16_t ntiles;      // stream tiles (ELL + other), = number of staged x segments (<= 256)
-    uint16_t nside;
-    uint16_t flags;       // CHF_*
-    uint16_t off_sidecol; // byte offsets from the start of the chunk (chunks are <= 32 KB)
+    uint16_t ntiles;       // stream tiles (ELL + other) of THIS chunk = staged x segments (<= 256)
+    uint16_t next_ntiles;  // counts of the lists at off_nextlist
+    uint16_t next_nside;
+    uint16_t off_nextlist; // byte offsets from the start of the chunk (chunks are < 64 KB)
     uint16_t off_odesc;
     uint16_t off_sidehdr;
     uint16_t off_sideval;
     uint32_t off_payload;
-    uint32_t nother;
-    uint32_t pad[2];
+    uint16_t next_flags;   // CHF_* of the next chunk's x staging
+    uint16_t nside;        // extracted nonzeros of THIS chunk
+    uint32_t issue_off16;  // TMA descriptor of the chunk this warp fetches into the stage this chunk
+    uint32_t issue_bytes;  //   frees: chunk index + stages * nw, {byte offset / 16, bytes}; 0 bytes = none
 };
 static_assert(sizeof(ChunkHeader) == 32, "ChunkHeader must be 32 bytes");
 constexpr uint32_t CHF_PARTIAL_X = 1u; // some x segment sticks out past colA (zero-filled staging path)
@@ -97,14 +102,21 @@ __host__ __device__ inline uint32_t ell_group_bytes(uint32_t nsr, uint32_t vs)
     return nsr * 16u * vs + pad16(nsr * 9u); // values | 8 B of nibbles + 1 B xsel per slot-row
 }
 
-// total size of a chunk from its counters (must match pack_kernel's layout exactly); `payload`
-// = sum over rows of ell_group_bytes + other payloads
-__host__ __device__ inline uint32_t chunk_layout_bytes(uint32_t nrows, uint32_t ntiles, uint32_t nother,
-                                                       uint32_t nsiderows, uint32_t nside, uint32_t payload, uint32_t vs)
+// bytes of the x-staging lists of a chunk with ntiles stream tiles and nside extracted nonzeros
+__host__ __device__ inline uint32_t list_bytes(uint32_t ntiles, uint32_t nside)
 {
-    return CHUNK_OFF_ROWS + 16u * nrows + pad16(4u * ntiles) + pad16(4u * nside) + pad16(8u * nother) +
-           pad16(SIDEHDR_BYTES * nsiderows) + pad16(vs * nside) + payload; // payload parts are multiples of 16
+    return pad16(4u * ntiles) + pad16(4u * nside);
 }
+// size of a chunk WITHOUT the trailing lists, from its counters (must match pack_kernel's layout
+// exactly); `payload` = sum over rows of ell_group_bytes + other payloads
+__host__ __device__ inline uint32_t chunk_main_bytes(uint32_t nrows, uint32_t nother, uint32_t nsiderows,
+                                                     uint32_t nside, uint32_t payload, uint32_t vs)
+{
+    return CHUNK_OFF_ROWS + 16u * nrows + pad16(8u * nother) + pad16(SIDEHDR_BYTES * nsiderows) + pad16(vs * nside) +
+           payload; // payload parts are multiples of 16
+}
+// head record of a warp's first chunk (plan.head): 16-byte header {ntiles | nside << 16, flags} + lists
+constexpr uint32_t HEAD_HDR_BYTES = 16;
 
 // one schedulable unit: a whole block row, or a piece of a long one
 struct PlanItem

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--xstage-bytes", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
+    ap.add_argument("--max-warps", type=int, default=0)
     a = ap.parse_args()
     t0 = time.time()
     if a.workload == "lap3d27":
@@ -49,7 +50,7 @@ def main():
     torch.cuda.synchronize()
     t_conv = time.time() - t0
     t0 = time.time()
-    plan = api.Plan(dm, a.chunk_bytes, a.xstage_bytes, a.ctas_per_sm, a.stages)
+    plan = api.Plan(dm, a.chunk_bytes, a.xstage_bytes, a.ctas_per_sm, a.stages, a.max_warps)
     torch.cuda.synchronize()
     t_plan = time.time() - t0
     pi, di = plan.info(), dm.info()
