@@ -92,7 +92,7 @@ def test_chunk_configurations_and_split_rows(name, cfg):
     """Tiny x-staging budgets force block rows to be cut into pieces (scratch + fix-up kernel)."""
     pi = check_matrix(CASES[name](), "f64", plan_kwargs=cfg)
     if cfg["xstage_bytes"] == 128 and name in ("rmat_12", "band_contig_8k", "uniform_8k", "lap3d27_24"):
-        assert pi.split_rows > 0 and pi.launches_per_spmv == 2
+        assert pi.split_rows > 0 and pi.launches_per_spmv >= 2
 
 
 @pytest.mark.parametrize("path", G.golden_files(), ids=os.path.basename)

@@ -854,7 +854,7 @@ int tilespmv_plan_get_info(const tilespmv_plan *plan, tilespmv_plan_info *info)
     info->algorithmic_bytes = plan->b_alg;
     info->csr_bytes = plan->b_csr;
     info->split_rows = plan->nsplit;
-    info->launches_per_spmv = plan->nchunks == 0 ? 0 : (plan->nsplit > 0 ? 2 : 1);
+    info->launches_per_spmv = plan->nchunks == 0 ? 0 : 1 + (plan->nsplit_small > 0 ? 1 : 0) + (plan->nsplit > plan->nsplit_small ? 1 : 0);
     info->grid = plan->grid;
     info->block = plan->block;
     info->smem_bytes = plan->smem;

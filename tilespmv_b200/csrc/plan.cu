@@ -175,8 +175,17 @@ __device__ void pack_other_tile(const PackArgs<T> &a, int t, int br, unsigned xs
     case TILESPMV_FMT_CSR:
     {
         const int o = a.csr_offset[t], po = a.csrptr_offset[t];
+        int maxlen = 0;
         for (int r = 0; r < TS; r++)
+        {
             pay[r] = r < rowlen ? a.Blockcsr_Ptr[po + r] : (unsigned char)nnz;
+            if (r < rowlen)
+            {
+                const int end = r + 1 < rowlen ? (int)a.Blockcsr_Ptr[po + r + 1] : nnz;
+                maxlen = max(maxlen, end - (int)a.Blockcsr_Ptr[po + r]);
+            }
+        }
+        w = (uint32_t)((maxlen + 3) >> 2); // trip count of the kernel's 4-lanes-per-row loop
         T *v = reinterpret_cast<T *>(pay + 16);
         unsigned char *ix = pay + 16 + pad8((uint32_t)nnz * (uint32_t)sizeof(T));
         for (int k = 0; k < nnz; k++)
@@ -496,7 +505,7 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
 {
     const uint32_t vs = (uint32_t)sizeof(T);
     const int T_ = dm->tilenum, tilem = dm->tilem, rowA = dm->rowA;
-    const uint32_t C = (uint32_t)P->chunk_bytes, X = (uint32_t)P->xstage_bytes;
+    uint32_t C = (uint32_t)P->chunk_bytes, X = (uint32_t)P->xstage_bytes; // 0 = chosen below from the row sizes
     ScanWorkspace ws;
 
     if (dm->fmt_hist[TILESPMV_FMT_HYB] > 0)
@@ -543,6 +552,43 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
     TSP_CUDA(cudaMemcpyAsync(row_s0.data(), d_row_s0.p, nb1 * sizeof(int), cudaMemcpyDeviceToHost, s));
     TSP_CUDA(cudaMemcpyAsync(tile_ptr.data(), dm->tile_ptr.p, nb1 * sizeof(int), cudaMemcpyDeviceToHost, s));
     TSP_CUDA(cudaStreamSynchronize(s));
+
+    // ---- 1b. chunk size.  A block row that does not fit a chunk is cut into pieces whose partial sums
+    //          take a second pass, so the stage should hold a typical block row (a 27-point stencil
+    //          row is 4 KB, a 37-per-row band 5.5 KB); larger stages mean fewer resident warps.
+    //          Pick the smallest candidate that leaves at most ~5 % of the stream bytes (or what the
+    //          largest candidate leaves, + 5 %) in rows that have to be cut.
+    if (C == 0)
+    {
+        const uint32_t cand[5] = {4096u, 5120u, 6144u, 7168u, 8192u};
+        double unfit[5] = {0, 0, 0, 0, 0}, total = 0;
+        for (int b = 0; b < tilem; b++)
+        {
+            const int ns = row_s0[b + 1] - row_s0[b];
+            const double bytes = (double)CHUNK_OFF_ROWS + 16.0 + (double)pad16(8u * (uint32_t)row_no[b]) + (ns > 0 ? 48.0 : 0.0) +
+                                 (double)vs * ns + (double)ell_group_bytes((uint32_t)row_nsr[b], vs) + (double)row_ob[b] +
+                                 (double)list_bytes((uint32_t)row_nt[b], (uint32_t)ns);
+            const double xb = (double)row_nt[b] * 16.0 * vs + (double)ns * vs;
+            total += bytes;
+            for (int k = 0; k < 5; k++)
+                if (bytes > cand[k] || xb > (X ? X : cand[k] * vs / 8u))
+                    unfit[k] += bytes;
+        }
+        int pick = 0;
+        if (total > 0)
+        {
+            const double limit = std::max(0.05, unfit[4] / total + 0.05);
+            while (pick < 4 && unfit[pick] / total > limit)
+                pick++;
+        }
+        C = cand[pick];
+        P->chunk_bytes = (int)C;
+    }
+    if (X == 0)
+    {
+        X = C * vs / 8u; // as many staged x values as a chunk of pure side entries can hold (C / 8 per fp64 ...)
+        P->xstage_bytes = (int)X;
+    }
 
     // ---- 2. greedy byte-bounded chunking over block rows ----
     std::vector<PlanItem> items;
@@ -695,6 +741,19 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
     }
     P->nchunks = nchunks;
     P->nsplit = (int64_t)split_tab.size() / 4;
+    {
+        // rows cut into many pieces (hub rows of power-law matrices) are combined by a CTA each, the
+        // others by one thread per row: small rows first in the table
+        std::vector<int> small, big;
+        for (size_t i = 0; i + 3 < split_tab.size(); i += 4)
+        {
+            std::vector<int> &dst = split_tab[i + 2] > SPLIT_BIG_SLOTS ? big : small;
+            dst.insert(dst.end(), split_tab.begin() + i, split_tab.begin() + i + 4);
+        }
+        P->nsplit_small = (int64_t)small.size() / 4;
+        split_tab = small;
+        split_tab.insert(split_tab.end(), big.begin(), big.end());
+    }
     P->nslots = nslots;
 
     // ---- 2b. launch shape and the lookahead distance nw.  Chunk c carries the x-staging lists of
@@ -868,13 +927,13 @@ int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tiles
     P->tilem = dm->tilem;
     P->nnz = dm->nnz;
     const int vs = dm->precision;
-    P->chunk_bytes = opts && opts->chunk_bytes ? opts->chunk_bytes : 4096;
-    P->xstage_bytes = opts && opts->xstage_bytes ? opts->xstage_bytes : (vs == 8 ? 2048 : 1024);
+    P->chunk_bytes = opts ? opts->chunk_bytes : 0;   // 0 = chosen from the row sizes (4..8 KB)
+    P->xstage_bytes = opts ? opts->xstage_bytes : 0; // 0 = follows chunk_bytes
     P->ctas_per_sm = opts ? opts->ctas_per_sm : 0;
     P->stages = opts ? opts->stages : 0;
     P->max_warps = opts ? opts->max_warps : 0;
-    if (P->chunk_bytes < 2560 || P->chunk_bytes > 32768 || (P->chunk_bytes & 127) || P->xstage_bytes < 16 * vs ||
-        P->xstage_bytes > 32768 || (P->xstage_bytes & 127))
+    if ((P->chunk_bytes != 0 && (P->chunk_bytes < 2560 || P->chunk_bytes > 32768 || (P->chunk_bytes & 127))) ||
+        (P->xstage_bytes != 0 && (P->xstage_bytes < 16 * vs || P->xstage_bytes > 32768 || (P->xstage_bytes & 127))))
     {
         set_error("plan: chunk_bytes must be a multiple of 128 in [2560, 32768], xstage_bytes a multiple of 128 in [%d, 32768]",
                   16 * vs);

@@ -4,6 +4,7 @@
 #include "stream.cuh"
 
 constexpr int TSP_MAX_PEERS = 8;
+constexpr int SPLIT_BIG_SLOTS = 8; // split rows with more pieces are combined by a whole CTA
 
 struct tilespmv_plan
 {
@@ -25,7 +26,7 @@ struct tilespmv_plan
 
     // block rows that were cut across chunks: partial sums land in scratch and are combined by the
     // fix-up kernel in a fixed order (deterministic, no atomics)
-    int64_t nsplit = 0, nslots = 0;
+    int64_t nsplit = 0, nsplit_small = 0, nslots = 0; // rows with <= SPLIT_BIG_SLOTS pieces come first in split_tab
     tsp::DevBuf scratch;   // T[nslots*16]
     tsp::DevBuf split_tab; // int4 {block row, first slot, #slots, rowlen} per split row
 

@@ -260,15 +260,26 @@ __device__ __forceinline__ void stage_x(uint32_t list_s, const uint32_t *list_g,
             cp_async_16_zfill(dst, valid ? x + col0 : x, (uint32_t)valid * (uint32_t)sizeof(T));
         }
     }
+    // gathers of the extracted nonzeros' x values, 4 x 32 per trip so that the column loads and the
+    // copies of a trip are all in flight together
     uint32_t dst2 = xb_s + (uint32_t)ntiles * (uint32_t)(TS * sizeof(T)) + (uint32_t)lane * (uint32_t)sizeof(T);
 #pragma unroll 1
-    for (int e = lane; e < nside; e += 32, dst2 += 32u * (uint32_t)sizeof(T))
+    for (int e0 = lane; e0 < nside + lane; e0 += 128, dst2 += 128u * (uint32_t)sizeof(T))
     {
-        const void *src = mad_wide(list_u32<GLOBAL>(list_s, list_g, sl + 4u * (uint32_t)(e - lane)), (uint32_t)sizeof(T), x);
-        if (sizeof(T) == 8)
-            cp_async_8(dst2, src);
-        else
-            cp_async_4(dst2, src);
+        uint32_t c[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            c[j] = e0 + 32 * j < nside ? list_u32<GLOBAL>(list_s, list_g, sl + 4u * (uint32_t)(e0 - lane + 32 * j)) : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (e0 + 32 * j < nside)
+            {
+                const void *src = mad_wide(c[j], (uint32_t)sizeof(T), x);
+                if (sizeof(T) == 8)
+                    cp_async_8(dst2 + (uint32_t)j * 32u * (uint32_t)sizeof(T), src);
+                else
+                    cp_async_4(dst2 + (uint32_t)j * 32u * (uint32_t)sizeof(T), src);
+            }
     }
 }
 
@@ -394,23 +405,37 @@ __device__ __forceinline__ void process_chunk(const unsigned char *st, uint32_t 
             case TILESPMV_FMT_CSR:
             {
                 const int nnz = (int)d.y;
-                const unsigned char *ptr = pay;
-                const T *cv = reinterpret_cast<const T *>(pay + 16);
                 const uint32_t vbytes = pad8((uint32_t)nnz * (uint32_t)sizeof(T));
-                const unsigned char *idx = pay + 16 + vbytes;
-                const int s0 = ptr[2 * p], s1 = ptr[2 * p + 1];
-                const int e1 = p == 7 ? nnz : (int)ptr[2 * p + 2];
+                // rows 2p / 2p+1 = entries [k0, s1) / [s1, e1); the 4 lanes of a row pair take every 4th
+                // entry.  w = max over the 16 rows of ceil(row length / 4): one loop for both rows, loads
+                // unconditional (a lane past its row's end reads neighbouring bytes of the chunk that
+                // are discarded), only the FMA is predicated.
+                const uint32_t pay_a = st_s + (uint32_t)(pay - st);
+                const uint32_t s1 = lds_u8(pay_a + 2u * p + 1u);
+                const uint32_t e1 = p == 7 ? (uint32_t)nnz : lds_u8(pay_a + 2u * p + 2u);
+                uint32_t k0 = lds_u8(pay_a + 2u * p) + (uint32_t)g, k1 = s1 + (uint32_t)g;
+                const uint32_t cv_a = pay_a + 16u, ix_a = cv_a + vbytes;
+                const uint32_t xs_a = xb_s + ((d.x >> 8) & 0xffu) * (TS * VS);
 #pragma unroll 1
-                for (int k = s0 + g; k < s1; k += 4)
+                for (int i = 0; i < w; i += 2)
                 {
-                    const unsigned b = idx[k >> 1];
-                    a0 = fma_t<T>(cv[k], xs[(k & 1) ? (b & 15u) : (b >> 4)], a0);
-                }
-#pragma unroll 1
-                for (int k = s1 + g; k < e1; k += 4)
-                {
-                    const unsigned b = idx[k >> 1];
-                    a1 = fma_t<T>(cv[k], xs[(k & 1) ? (b & 15u) : (b >> 4)], a1);
+                    // parity of k0 / k1 is the same for both trips of the unrolled body (stride 4)
+                    const uint32_t sh0 = (k0 & 1u) ? 0u : 4u, sh1 = (k1 & 1u) ? 0u : 4u;
+                    const uint32_t va0 = cv_a + k0 * VS, va1 = cv_a + k1 * VS;
+                    const uint32_t ia0 = ix_a + (k0 >> 1), ia1 = ix_a + (k1 >> 1);
+#pragma unroll
+                    for (uint32_t j = 0; j < 2; j++)
+                    {
+                        const T v0 = SL<T>::ld(va0 + j * (4u * VS)), v1 = SL<T>::ld(va1 + j * (4u * VS));
+                        const uint32_t n0 = (lds_u8(ia0 + 2u * j) >> sh0) & 15u, n1 = (lds_u8(ia1 + 2u * j) >> sh1) & 15u;
+                        const T x0 = SL<T>::ld(mad_u32(n0, VS, xs_a)), x1 = SL<T>::ld(mad_u32(n1, VS, xs_a));
+                        if (k0 + 4u * j < s1)
+                            a0 = fma_t<T>(v0, x0, a0);
+                        if (k1 + 4u * j < e1)
+                            a1 = fma_t<T>(v1, x1, a1);
+                    }
+                    k0 += 8u;
+                    k1 += 8u;
                 }
                 pay += pad16(16u + vbytes + pad8(((uint32_t)nnz + 1u) / 2u));
                 break;
@@ -645,6 +670,42 @@ __global__ void __launch_bounds__(128)
         a.peers[p][row_offset + (long long)row] = sum;
 }
 
+// the same for rows cut into many pieces: one CTA per row, 16 slot lanes x 16 rows, fixed-order
+// shared-memory tree (deterministic)
+template <class T>
+__global__ void __launch_bounds__(256)
+    split_fixup_big_kernel(const int4 *__restrict__ tab, const T *__restrict__ scratch, T *__restrict__ y, int npeers,
+                           long long row_offset, SpmvArgs<T> a)
+{
+    __shared__ T part[16][TS + 1];
+    const int4 e = tab[blockIdx.x]; // block row, first slot, #slots, rowlen
+    const int r = threadIdx.x & 15, q = threadIdx.x >> 4;
+    T s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    int k = q;
+    for (; k + 48 < e.z; k += 64)
+    {
+        s0 += scratch[(size_t)(e.y + k) * TS + r];
+        s1 += scratch[(size_t)(e.y + k + 16) * TS + r];
+        s2 += scratch[(size_t)(e.y + k + 32) * TS + r];
+        s3 += scratch[(size_t)(e.y + k + 48) * TS + r];
+    }
+    for (; k < e.z; k += 16)
+        s0 += scratch[(size_t)(e.y + k) * TS + r];
+    part[q][r] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (q == 0 && r < e.w)
+    {
+        T sum = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            sum += part[i][r];
+        const size_t row = (size_t)e.x * TS + r;
+        y[row] = sum;
+        for (int p = 0; p < npeers; p++)
+            a.peers[p][row_offset + (long long)row] = sum;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -759,10 +820,13 @@ static int plan_launch_t(tilespmv_plan *P, const T *x, T *y, cudaStream_t s)
             return TILESPMV_ERR_CUDA;
         }
     }
-    if (P->nsplit > 0)
+    if (P->nsplit > P->nsplit_small)
+        TSP_LAUNCH((split_fixup_big_kernel<T>), (unsigned)(P->nsplit - P->nsplit_small), 256, 0, s,
+                   P->split_tab.as<int4>() + P->nsplit_small, P->scratch.as<T>(), y, P->npeers, (long long)P->row_offset, a);
+    if (P->nsplit_small > 0)
     {
-        const long long threads = P->nsplit * TS;
-        TSP_LAUNCH((split_fixup_kernel<T>), grid_for((size_t)threads, 128), 128, 0, s, P->split_tab.as<int4>(), (long long)P->nsplit,
+        const long long threads = P->nsplit_small * TS;
+        TSP_LAUNCH((split_fixup_kernel<T>), grid_for((size_t)threads, 128), 128, 0, s, P->split_tab.as<int4>(), (long long)P->nsplit_small,
                    P->scratch.as<T>(), y, P->npeers, (long long)P->row_offset, a);
     }
     return TILESPMV_OK;

@@ -44,7 +44,12 @@ if nchunks:
     hdr = rows[1]
     iS, iI, iSrc = hdr.index('Warp Stall Sampling (All Samples)'), hdr.index('Instructions Executed'), hdr.index('Source')
     iW, iWi = hdr.index('L1 Wavefronts Shared'), hdr.index('L1 Wavefronts Shared Ideal')
-    data = rows[2:]
+    data = []
+    for r in rows[2:]:
+        if r and r[0] == 'Kernel Name':  # second kernel of the report: only the first one is listed
+            break
+        if len(r) > max(iS, iI) and r[iS] != '':
+            data.append(r)
     tot_s = sum(int(r[iS]) for r in data)
     tot_i = sum(int(r[iI]) for r in data)
     print(f"total samples {tot_s}, warp instructions {tot_i} = {tot_i / nchunks:.1f} per chunk")
