@@ -462,3 +462,20 @@ int64_t tsgen_seven_formats(int *rowptr, int *colidx, double *val)
         rowptr[32] = (int)p;
     return p;
 }
+
+/* Fast Matrix Market writer ("coordinate real general", row-major, 1-based): inputs for the
+ * reference's own driver (./test -d 0 file.mtx).  Values are written with %.17g. Returns 0 / -1. */
+#include <stdio.h>
+int tsgen_write_mtx(const char *path, int m, int n, const int *rowptr, const int *colidx, const double *val)
+{
+    FILE *f = fopen(path, "w");
+    if (!f)
+        return -1;
+    static char buf[1 << 22];
+    setvbuf(f, buf, _IOFBF, sizeof(buf));
+    fprintf(f, "%%%%MatrixMarket matrix coordinate real general\n%d %d %d\n", m, n, rowptr[m]);
+    for (int i = 0; i < m; i++)
+        for (int j = rowptr[i]; j < rowptr[i + 1]; j++)
+            fprintf(f, "%d %d %.17g\n", i + 1, colidx[j] + 1, val[j]);
+    return fclose(f) == 0 ? 0 : -1;
+}

@@ -144,3 +144,15 @@ def write_mtx(path, m, n, rowptr, colidx, val, column_major=True):
         f.write(f"{m} {n} {len(cols)}\n")
         for k in order:
             f.write(f"{rows[k] + 1} {cols[k] + 1} {float(val[k])!r}\n")
+
+
+def write_mtx_fast(path, m, n, rowptr, colidx, val):
+    """C writer (row-major order) for large inputs of the reference's own driver."""
+    rp = np.ascontiguousarray(rowptr, np.int32)
+    ci = np.ascontiguousarray(colidx, np.int32)
+    v = np.ascontiguousarray(val, np.float64)
+    L = _L()
+    L.tsgen_write_mtx.restype = C.c_int
+    rc = L.tsgen_write_mtx(C.c_char_p(path.encode()), C.c_int(m), C.c_int(n), *_ptrs(rp, ci, v))
+    if rc != 0:
+        raise OSError(f"cannot write {path}")
