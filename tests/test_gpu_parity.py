@@ -175,3 +175,45 @@ def test_config1_lap2d_1024_against_oracle():
     from tilespmv_b200 import generators as g
     pi = check_matrix(g.lap2d(1024, val_mode=1), "f64")
     assert pi.algorithmic_bytes == 67197320  # B_alg(C1) of SURVEY.md Appendix D
+
+
+def test_config2_lap3d27_160_against_oracle_full_size():
+    """BASELINE config 2 (the bench workload): 3-D 27-point Laplacian 160^3, conversion bit-exact against the
+    oracle, y bit-exact on integer data and within 1e-12 on real data, at full size."""
+    from tilespmv_b200 import generators as g
+    pi = check_matrix(g.lap3d27(160, val_mode=1), "f64")
+    assert pi.algorithmic_bytes == 1037093192  # B_alg(C2) of SURVEY.md Appendix D
+    assert pi.split_rows == 0 and pi.launches_per_spmv == 1
+
+
+@pytest.mark.parametrize("name,precision", [("banded_1m", "f64"), ("rmat_18", "f32"), ("uniform_2m", "f64"),
+                                            ("band_contig_1m", "f32")])
+def test_reduced_configs_3_4_5_and_size_independent_properties(name, precision):
+    """Configs 3/4/5 at the largest size the oracle finishes in seconds, plus properties that need no oracle:
+    linearity A(a*x + b*z) = a*A*x + b*A*z and y(e_j) = column j."""
+    from tilespmv_b200 import generators as g
+    case = {"banded_1m": lambda: g.banded(1 << 20, val_mode=0), "rmat_18": lambda: g.rmat(18, val_mode=0),
+            "uniform_2m": lambda: g.uniform(1 << 21, val_mode=1), "band_contig_1m": lambda: g.band_contig(1 << 20, val_mode=0)}[name]()
+    check_matrix(case, precision)
+    m, n, rp, ci, v = case
+    dt = np.float64 if precision == "f64" else np.float32
+    v = v.astype(dt)
+    dm = api.DeviceTileMatrix.from_csr(m, n, rp, ci, v)
+    plan = api.Plan(dm)
+    rng = np.random.default_rng(3)
+    x, z = rng.uniform(-1, 1, n).astype(dt), rng.uniform(-1, 1, n).astype(dt)
+    a, b = dt(0.75), dt(-1.5)
+    lhs = plan.spmv_host((a * x + b * z).astype(dt)).astype(np.float64)
+    rhs = a * plan.spmv_host(x).astype(np.float64) + b * plan.spmv_host(z).astype(np.float64)
+    ora = O.Oracle(precision)
+    scale = ora.csr_abs_spmv(m, rp, ci, v, (np.abs(x) + np.abs(z)).astype(dt)).astype(np.float64) * 2.25
+    assert np.all(np.abs(lhs - rhs) <= 8 * TOL[precision] * np.maximum(scale, 1e-300))
+    j = int(ci[len(ci) // 2])  # a column that certainly has an entry
+    e = np.zeros(n, dt)
+    e[j] = 1
+    col = plan.spmv_host(e)
+    want = np.zeros(m, np.float64)
+    rows = np.repeat(np.arange(m), np.diff(rp))
+    sel = ci == j
+    np.add.at(want, rows[sel], v[sel].astype(np.float64))
+    assert np.array_equal(col.astype(np.float64), want.astype(dt).astype(np.float64))
