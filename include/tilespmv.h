@@ -196,6 +196,11 @@ typedef struct tilespmv_plan tilespmv_plan;
 
 /* flags of tilespmv_convert */
 #define TILESPMV_CSR_ON_DEVICE 1 /* rowptr / colidx / val are device pointers */
+/* Non-default: switch on the reference's dormant HYB selection rule (csr2tile.h:279-316, commented out
+ * upstream): a tile that would be CSR becomes HYB (format 3) when its row-length variation is >= 1.0 and the
+ * I/O-cost walk leaves <= 4 spilled entries.  The result is bit-exact with the reference built with that
+ * rule un-commented (oracle/Makefile, target ref_hyb).  Without this flag format 3 is never produced. */
+#define TILESPMV_ENABLE_HYB 2
 
 /*
  * GPU csr2tile: CSR (host pointers, or device pointers with TILESPMV_CSR_ON_DEVICE) -> a

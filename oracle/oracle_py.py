@@ -143,10 +143,13 @@ class Oracle:
 
     kind = "port"
 
-    def __init__(self, precision="f64"):
+    def __init__(self, precision="f64", enable_hyb=False):
+        """enable_hyb: the dormant HYB rule of csr2tile.h:279-316 switched on (pinned against the
+        "refhyb" variant of Reference); default = the reference as shipped."""
         _ensure_built()
         self.L = _Lib(os.path.join(HERE, f"libtilespmv_oracle_{precision}.so"), "oracle", precision)
         self.val_dtype = self.L.val_dtype
+        self.enable_hyb = bool(enable_hyb)
 
     def threads(self):
         return self.L.fn("omp_max_threads", C.c_int)()
@@ -156,6 +159,7 @@ class Oracle:
         rowptr = np.ascontiguousarray(rowptr, np.int32)
         colidx = np.ascontiguousarray(colidx, np.int32)
         val = np.ascontiguousarray(val, self.val_dtype)
+        self.L.fn("set_enable_hyb")(C.c_int(1 if self.enable_hyb else 0))
         self.L.fn("tile_create")(C.byref(M), C.c_int(rowA), C.c_int(colA), C.c_int(len(colidx)),
                                  _p(rowptr, C.c_int), _p(colidx, C.c_int), _p(val, self.L.val_ctype))
         return M
@@ -227,8 +231,8 @@ class Oracle:
         return 0, out
 
 
-def ref_available(precision="f64"):
-    return os.path.exists(os.path.join(HERE, "_ref", f"libtilespmv_ref_{precision}.so"))
+def ref_available(precision="f64", variant="ref"):
+    return os.path.exists(os.path.join(HERE, "_ref", f"libtilespmv_{variant}_{precision}.so"))
 
 
 class Reference:
@@ -236,8 +240,10 @@ class Reference:
 
     kind = "reference"
 
-    def __init__(self, precision="f64"):
-        self.L = _Lib(os.path.join(HERE, "_ref", f"libtilespmv_ref_{precision}.so"), "ref", precision)
+    def __init__(self, precision="f64", variant="ref"):
+        """variant "ref": the unmodified reference; "refhyb": the same sources with the dormant HYB
+        selection rule of csr2tile.h:308-317 un-commented (oracle/Makefile, target ref_hyb)."""
+        self.L = _Lib(os.path.join(HERE, "_ref", f"libtilespmv_{variant}_{precision}.so"), "ref", precision)
         self.val_dtype = self.L.val_dtype
 
     def threads(self):

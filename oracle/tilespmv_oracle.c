@@ -198,9 +198,15 @@ static inline int local_row_of(int j, const int *rowptr, int row0, int rowlen)
  * cnt[] = nnz per local row, ccnt[] = nnz per local column.
  * Outputs: format code, stored slots, ELL width, #dense rows, #dense cols.
  */
+/* 0 (default) = the reference as shipped: format 3 never chosen.  1 = the dormant rule of csr2tile.h:279-316
+   (commented out upstream) switched on; pinned against oracle/_ref/libtilespmv_refhyb_*.so. */
+static int g_enable_hyb = 0;
+void oracle_set_enable_hyb(int on) { g_enable_hyb = on; }
+
 static void classify_tile(int nnz, const unsigned char *cnt, const unsigned char *ccnt, int rowlen,
-                          int collen, int *fmt, int *slots, int *width, int *ndr, int *ndc)
+                          int collen, int *fmt, int *slots, int *width, int *ndr, int *ndc, int *spill)
 {
+    *spill = 0;
     *width = 0;
     *ndr = 0;
     *ndc = 0;
@@ -288,6 +294,38 @@ static void classify_tile(int nnz, const unsigned char *cnt, const unsigned char
         *width = wmax;
         *slots = wmax * rowlen;
         return;
+    }
+    if (g_enable_hyb)
+    {
+        /* I/O-cost walk of :279-306: shrink the ELL width while bytes (value + nibble per ELL slot, value +
+           index byte per spilled entry) keep going down; HYB when cv >= 1.0 and <= 4 entries spill (:308) */
+        const int vs = (int)sizeof(val_t);
+        int hybwidth = wmax, prior_spill = 0;
+        int ioprior = wmax * rowlen * vs + (wmax * rowlen) / 2 + ((wmax * rowlen) % 2);
+        for (int wi = wmax - 1; wi > 0; wi--)
+        {
+            int next_spill = 0;
+            for (int r = 0; r < rowlen; r++)
+                if (cnt[r] > wi)
+                    next_spill += cnt[r] - wi;
+            int ionext = wi * rowlen * vs + (wi * rowlen) / 2 + ((wi * rowlen) % 2) + next_spill * (vs + 1);
+            if (ioprior <= ionext)
+            {
+                hybwidth = wi + 1;
+                break;
+            }
+            hybwidth = wi;
+            ioprior = ionext;
+            prior_spill = next_spill;
+        }
+        if (cv >= 1.0 && prior_spill <= 4)
+        {
+            *fmt = 3;
+            *width = hybwidth;
+            *spill = prior_spill;
+            *slots = prior_spill + hybwidth * rowlen;
+            return;
+        }
     }
     /* the HYB branch is commented out upstream (:308-316): everything else is CSR */
     *fmt = 0;
@@ -495,9 +533,9 @@ void oracle_tile_create(oracle_tile_matrix *M, int rowA, int colA, int nnzA, con
             memset(ccnt, 0, sizeof(ccnt));
             for (int p = M->tile_nnz[t]; p < M->tile_nnz[t + 1]; p++)
                 ccnt[colidx[perm[p]] - M->tile_columnidx[t] * TS]++;
-            int fmt, slots, width, ndr, ndc;
+            int fmt, slots, width, ndr, ndc, spill;
             classify_tile(nnz, rowcnt + (size_t)t * TS, ccnt, rowlen, collen, &fmt, &slots, &width,
-                          &ndr, &ndc);
+                          &ndr, &ndc, &spill);
             M->Format[t] = (char)fmt;
             M->blknnz[t] = slots;
             M->tilewidth[t] = (char)width;
@@ -513,6 +551,11 @@ void oracle_tile_create(oracle_tile_matrix *M, int rowA, int colA, int nnzA, con
                 break;
             case 2:
                 M->ell_offset[t] = slots;
+                break;
+            case 3: /* :309-316 */
+                M->hyb_offset[t] = slots;
+                M->hyb_coocount[t] = spill;
+                M->new_coocount[t] = spill;
                 break;
             case 4:
                 M->dns_offset[t] = slots;
@@ -547,6 +590,10 @@ void oracle_tile_create(oracle_tile_matrix *M, int rowA, int colA, int nnzA, con
             case 2:
                 M->ellsize += M->blknnz[t];
                 break;
+            case 3: /* :776-779 */
+                M->hybsize += M->blknnz[t];
+                M->hybellsize += M->tilewidth[t] * rowlen;
+                break;
             case 4:
                 M->dnssize += M->blknnz[t];
                 break;
@@ -579,7 +626,10 @@ void oracle_tile_create(oracle_tile_matrix *M, int rowA, int colA, int nnzA, con
     M->Blockell_Val = (val_t *)zalloc(M->ellsize, sizeof(val_t));
     M->ell_compressedIdx = (unsigned char *)zalloc((M->ellsize + 1) / 2, 1);
     M->Blockhyb_Val = (val_t *)zalloc(M->hybellsize + M->hybcoosize, sizeof(val_t));
-    M->hybIdx = (unsigned char *)zalloc((M->hybellsize + 1) / 2 + M->hybcoosize, 1);
+    /* the reference sizes hybIdx ceil(hybellsize/2) + hybcoosize (:840-841) but fills it with per-tile rounding
+       (:994-1004): + one spare byte per tile row so that odd ELL parts in a ragged last block row stay in bounds */
+    M->hybIdx = (unsigned char *)zalloc((M->hybellsize + 1) / 2 + M->hybcoosize + T + 1, 1);
+    unsigned char *hyb_lc = (unsigned char *)zalloc(M->hybsize, 1);
     M->Blockdense_Val = (val_t *)zalloc(M->dnssize, sizeof(val_t));
     M->Blockdenserow_Val = (val_t *)zalloc(M->dnsrowsize, sizeof(val_t));
     M->denserowid = (char *)zalloc(M->dnsrowptr[T], 1);
@@ -611,7 +661,7 @@ void oracle_tile_create(oracle_tile_matrix *M, int rowA, int colA, int nnzA, con
                 }
             }
             int r = 0;
-            int ndr = 0;
+            int ndr = 0, nspill = 0;
             for (int k = 0; k < n; k++)
             {
                 while (r + 1 < rowlen && k >= rs[r + 1])
@@ -636,6 +686,26 @@ void oracle_tile_create(oracle_tile_matrix *M, int rowA, int colA, int nnzA, con
                     M->Blockell_Val[M->ell_offset[t] + kr * rowlen + r] = val[j];
                     ell_lc[M->ell_offset[t] + kr * rowlen + r] = (unsigned char)lc;
                     break;
+                case 3: /* :505-548: ELL part slot-major, then the spilled entries in row order; the spilled
+                           entries are ALSO handed to the side matrix (:538-545) */
+                {
+                    const int w = M->tilewidth[t], base = M->hyb_offset[t];
+                    if (kr < w)
+                    {
+                        M->Blockhyb_Val[base + kr * rowlen + r] = val[j];
+                        hyb_lc[base + kr * rowlen + r] = (unsigned char)lc;
+                    }
+                    else
+                    {
+                        M->Blockhyb_Val[base + w * rowlen + nspill] = val[j];
+                        hyb_lc[base + w * rowlen + nspill] = (unsigned char)((r << 4) + lc);
+                        side_v[M->new_coocount[t] + nspill] = val[j];
+                        side_r[M->new_coocount[t] + nspill] = b * TS + r;
+                        side_c[M->new_coocount[t] + nspill] = tc * TS + lc;
+                        nspill++;
+                    }
+                    break;
+                }
                 case 4:
                     M->Blockdense_Val[M->dns_offset[t] + lc * rowlen + r] = val[j];
                     break;
@@ -660,6 +730,22 @@ void oracle_tile_create(oracle_tile_matrix *M, int rowA, int colA, int nnzA, con
 
     pack_nibbles(csr_lc, M->csr_compressedIdx, M->csrsize);
     pack_nibbles(ell_lc, M->ell_compressedIdx, M->ellsize);
+    /* HYB indices tile by tile (:984-1008): nibble parity restarts in every tile, spill bytes follow */
+    {
+        int o_idx = 0;
+        for (int t = 0; t < T; t++)
+        {
+            if (M->Format[t] != 3)
+                continue;
+            const int spill = M->hyb_coocount[t + 1] - M->hyb_coocount[t];
+            const int ell = M->hyb_offset[t + 1] - M->hyb_offset[t] - spill;
+            pack_nibbles(hyb_lc + M->hyb_offset[t], M->hybIdx + o_idx, ell);
+            o_idx += (ell + 1) / 2;
+            memcpy(M->hybIdx + o_idx, hyb_lc + M->hyb_offset[t] + ell, spill);
+            o_idx += spill;
+        }
+    }
+    free(hyb_lc);
 
     /* ---- deferred-COO side CSR over global rows / cols (csr2tile.h:899-960) ---- */
     M->deferredcoo_val = (val_t *)zalloc(M->coototal, sizeof(val_t));

@@ -40,6 +40,67 @@ def _empty_rows(m=64, n=64):
     return m, n, rp, np.array(cols, np.int32), (np.arange(len(cols)) % 10).astype(np.float64)
 
 
+def hyb_rich(nbr=48, ntc=40, rowA=None, colA=None, seed=11, val_mode=1):
+    """Tiles shaped to hit the reference's dormant HYB rule (csr2tile.h:279-316: row-length variation >= 1.0
+    and <= 4 entries past the I/O-optimal ELL width) next to near misses, ELL, CSR and COO tiles."""
+    rng = np.random.default_rng(seed)
+    rowA = nbr * 16 if rowA is None else rowA
+    colA = ntc * 16 if colA is None else colA
+    rows = [dict() for _ in range(rowA)]  # global row -> {col: 1}
+    for b in range(nbr):
+        rowlen = min(16, rowA - b * 16)
+        if rowlen <= 0:
+            break
+        for tc in rng.choice(ntc, size=min(ntc, 6), replace=False):
+            collen = min(16, colA - tc * 16)
+            if collen <= 0:
+                continue
+            kind = rng.integers(0, 5)
+            cells = set()
+            if kind <= 1:  # k rows with one entry + up to 5 extras in one or two rows
+                k = int(rng.integers(min(8, rowlen), rowlen + 1))
+                for r in rng.choice(rowlen, size=k, replace=False):
+                    cells.add((int(r), int(rng.integers(collen))))
+                hot = rng.choice(rowlen, size=int(rng.integers(1, 3)), replace=False)
+                for _ in range(int(rng.integers(0, 6))):
+                    cells.add((int(rng.choice(hot)), int(rng.integers(collen))))
+            elif kind == 2:  # scattered
+                for _ in range(int(rng.integers(13, 48))):
+                    cells.add((int(rng.integers(rowlen)), int(rng.integers(collen))))
+            elif kind == 3:  # even rows: ELL
+                w = int(rng.integers(1, 4))
+                for r in range(rowlen):
+                    for c in rng.choice(collen, size=min(w, collen), replace=False):
+                        cells.add((r, int(c)))
+            else:  # very sparse: COO
+                for _ in range(int(rng.integers(1, 12))):
+                    cells.add((int(rng.integers(rowlen)), int(rng.integers(collen))))
+            for r, c in cells:
+                rows[b * 16 + r][tc * 16 + c] = 1
+    rp = np.zeros(rowA + 1, np.int32)
+    cols = []
+    for i, d in enumerate(rows):
+        cols.extend(sorted(d))
+        rp[i + 1] = len(cols)
+    ci = np.array(cols, np.int32)
+    if val_mode == 1:
+        v = (np.arange(len(ci)) % 10).astype(np.float64)
+    else:
+        v = rng.uniform(-1, 1, len(ci))
+    return rowA, colA, rp, ci, v
+
+
+# inputs for the non-default HYB rule (TILESPMV_ENABLE_HYB), checked against the reference built with that rule
+HYB_CASES = {
+    "hyb_rich": lambda: hyb_rich(),
+    "hyb_rich_real": lambda: hyb_rich(seed=12, val_mode=0),
+    "hyb_ragged": lambda: hyb_rich(nbr=12, ntc=12, rowA=12 * 16 - 3, colA=12 * 16 - 5, seed=19),  # a HYB tile in the 13-row last block row
+    "rmat_12": lambda: g.rmat(12, val_mode=1),
+    "rmat_10_real": lambda: g.rmat(10, val_mode=0),
+    "seven_formats": lambda: g.seven_formats(),
+    "banded_2k_real": lambda: g.banded(2048, val_mode=0),
+}
+
 CASES = {
     "seven_formats": lambda: g.seven_formats(),
     "lap2d_64": lambda: g.lap2d(64, val_mode=1),

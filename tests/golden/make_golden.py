@@ -15,19 +15,24 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from oracle import oracle_py as O  # noqa: E402
-from tests.cases import CASES, x_for  # noqa: E402
+from tests.cases import CASES, HYB_CASES, x_for  # noqa: E402
 
 GOLDEN = ["seven_formats", "lap2d_64", "lap3d27_24", "banded_2k_real", "band_contig_8k", "rmat_10_real",
           "uniform_2k", "rmat_unsorted", "ragged_band", "ragged_seven", "empty_rows"]
 
 
+# fixtures of the NON-DEFAULT HYB rule: produced by the reference built with csr2tile.h:308-317 un-commented
+# (oracle/Makefile, target ref_hyb) into tests/golden/hyb/
+GOLDEN_HYB = ["hyb_rich", "hyb_rich_real", "hyb_ragged", "rmat_10_real"]
+
+
 def main():
     for precision in ("f64", "f32"):
-        ref = O.Reference(precision)
-        for name in GOLDEN:
-            if precision == "f32" and name not in ("seven_formats", "banded_2k_real", "ragged_seven"):
+        for name, variant in [(n, "ref") for n in GOLDEN] + [(n, "refhyb") for n in GOLDEN_HYB]:
+            ref = O.Reference(precision, variant)
+            if precision == "f32" and name not in ("seven_formats", "banded_2k_real", "ragged_seven", "hyb_rich"):
                 continue
-            m, n, rp, ci, v = CASES[name]()
+            m, n, rp, ci, v = (CASES if variant == "ref" else HYB_CASES)[name]()
             v = v.astype(ref.val_dtype)
             M = ref.tile_create(m, n, rp, ci, v)
             arrs = ref.arrays(M, m)
@@ -38,7 +43,9 @@ def main():
                    "rowblkblock": np.array([sched[0]]), "blkcoostylerowidx": sched[1],
                    "blkcoostylerowidx_colstart": sched[2], "blkcoostylerowidx_colstop": sched[3]}
             out.update({"tm_" + k: a for k, a in arrs.items()})
-            path = os.path.join(HERE, f"{name}_{precision}.npz")
+            path = os.path.join(HERE, f"{name}_{precision}.npz") if variant == "ref" else \
+                os.path.join(HERE, "hyb", f"{name}_{precision}.npz")
+            os.makedirs(os.path.dirname(path), exist_ok=True)
             np.savez_compressed(path, **out)
             print(path, os.path.getsize(path))
 

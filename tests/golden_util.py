@@ -6,9 +6,10 @@ import numpy as np
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def golden_files(precision=None):
+def golden_files(precision=None, hyb=False):
+    """hyb=True: the fixtures of the non-default HYB rule (tests/golden/hyb/)."""
     pat = f"*_{precision}.npz" if precision else "*.npz"
-    return sorted(glob.glob(os.path.join(GOLDEN_DIR, pat)))
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "hyb" if hyb else "", pat)))
 
 
 def load(path):

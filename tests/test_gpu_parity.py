@@ -35,14 +35,14 @@ def assert_y_close(y, y_ref, scale, precision, what=""):
                            f"want {y_ref[bad[:8]]}")
 
 
-def check_matrix(case, precision, plan_kwargs=None, exact_modes=(1,), real_modes=(0,)):
+def check_matrix(case, precision, plan_kwargs=None, exact_modes=(1,), real_modes=(0,), enable_hyb=False):
     m, n, rp, ci, v = case
-    ora = O.Oracle(precision)
+    ora = O.Oracle(precision, enable_hyb=enable_hyb)
     v = v.astype(ora.val_dtype)
     Mo = ora.tile_create(m, n, rp, ci, v)
     want = ora.arrays(Mo, m)
     # --- conversion on the GPU, bit-exact ---
-    dm = api.DeviceTileMatrix.from_csr(m, n, rp, ci, v)
+    dm = api.DeviceTileMatrix.from_csr(m, n, rp, ci, v, enable_hyb=enable_hyb)
     Mg = dm.export()
     G.assert_tile_arrays_equal(Mg.arrays(), want, "Tile_matrix.")
     info = dm.info()

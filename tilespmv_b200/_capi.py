@@ -15,6 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 
 F64, F32 = 8, 4
 CSR_ON_DEVICE = 1
+ENABLE_HYB = 2
 OK = 0
 ERR_NODEVICE = -5
 

@@ -121,19 +121,21 @@ class DeviceTileMatrix:
         self.val_dtype = np.float64 if precision == F64 else np.float32
 
     @classmethod
-    def from_csr(cls, rowA, colA, rowptr, colidx, val, on_device=False, precision=None):
-        """GPU csr2tile.  Host numpy arrays, or raw device pointers (ints) with on_device=True."""
+    def from_csr(cls, rowA, colA, rowptr, colidx, val, on_device=False, precision=None, enable_hyb=False):
+        """GPU csr2tile.  Host numpy arrays, or raw device pointers (ints) with on_device=True.
+        enable_hyb switches on the reference's dormant HYB rule (csr2tile.h:279-316); default off."""
         L = _capi.load()
         h = C.c_void_p()
+        hyb = _capi.ENABLE_HYB if enable_hyb else 0
         if on_device:
             check(L.tilespmv_convert(precision, rowA, colA, C.c_void_p(rowptr), C.c_void_p(colidx),
-                                     C.c_void_p(val), _capi.CSR_ON_DEVICE, C.byref(h)), "tilespmv_convert")
+                                     C.c_void_p(val), _capi.CSR_ON_DEVICE | hyb, C.byref(h)), "tilespmv_convert")
         else:
             precision = _precision_of(val)
             rp = np.ascontiguousarray(rowptr, np.int32)
             ci = np.ascontiguousarray(colidx, np.int32)
             v = np.ascontiguousarray(val)
-            check(L.tilespmv_convert(precision, rowA, colA, _ptr(rp), _ptr(ci), _ptr(v), 0, C.byref(h)),
+            check(L.tilespmv_convert(precision, rowA, colA, _ptr(rp), _ptr(ci), _ptr(v), hyb, C.byref(h)),
                   "tilespmv_convert")
         return cls(h, precision, rowA, colA)
 

@@ -302,8 +302,10 @@ static int convert_entry(int precision, int rowA, int colA, const int *rowptr, c
     if (!d)
         return TILESPMV_ERR_ALLOC;
     int rc = precision == TILESPMV_F64
-                 ? convert_csr_to_tiles<double>(rowA, colA, d_rowptr, d_colidx, static_cast<const double *>(d_val), d, 0)
-                 : convert_csr_to_tiles<float>(rowA, colA, d_rowptr, d_colidx, static_cast<const float *>(d_val), d, 0);
+                 ? convert_csr_to_tiles<double>(rowA, colA, d_rowptr, d_colidx, static_cast<const double *>(d_val), d, 0,
+                                                (flags & TILESPMV_ENABLE_HYB) != 0)
+                 : convert_csr_to_tiles<float>(rowA, colA, d_rowptr, d_colidx, static_cast<const float *>(d_val), d, 0,
+                                               (flags & TILESPMV_ENABLE_HYB) != 0);
     if (rc != TILESPMV_OK)
     {
         delete d;

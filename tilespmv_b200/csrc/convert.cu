@@ -107,9 +107,11 @@ __global__ void __launch_bounds__(128)
     classify_kernel(int T, const int *__restrict__ tile_nnz, const int *__restrict__ tile_br,
                     const int *__restrict__ tile_columnidx, unsigned char *__restrict__ rowstart,
                     const uint32_t *__restrict__ perm, const int *__restrict__ colidx, int tilem, int tilen,
-                    int rowA, int colA, char *__restrict__ Format, int *__restrict__ slots_out,
+                    int rowA, int colA, int hyb_vs, char *__restrict__ Format, int *__restrict__ slots_out,
                     char *__restrict__ width_out, int *__restrict__ nd_out)
 {
+    // hyb_vs: 0 = the reference default (HYB never chosen); sizeof(MAT_VAL_TYPE) = the dormant rule of
+    // csr2tile.h:279-316 switched on (TILESPMV_ENABLE_HYB)
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T)
         return;
@@ -250,6 +252,36 @@ __global__ void __launch_bounds__(128)
         {
             fmt = TILESPMV_FMT_CSR; // the HYB branch is commented out upstream (:308-316)
             slots = nnz;
+            if (hyb_vs)
+            {
+                // I/O-cost walk of :279-306: shrink the ELL width while the bytes (values + nibbles of the
+                // ELL part, value + index byte per spilled entry) keep going down
+                int hybwidth = wmax, spill = 0;
+                int ioprior = wmax * rowlen * hyb_vs + (wmax * rowlen) / 2 + ((wmax * rowlen) & 1);
+                for (int wi = wmax - 1; wi > 0; wi--)
+                {
+                    int coonext = 0;
+                    for (int r = 0; r < rowlen; r++)
+                        if (cnt[r] > wi)
+                            coonext += cnt[r] - wi;
+                    const int ionext = wi * rowlen * hyb_vs + (wi * rowlen) / 2 + ((wi * rowlen) & 1) + coonext * (hyb_vs + 1);
+                    if (ioprior <= ionext)
+                    {
+                        hybwidth = wi + 1;
+                        break;
+                    }
+                    hybwidth = wi;
+                    ioprior = ionext;
+                    spill = coonext;
+                }
+                if (cv >= 1.0 && spill <= 4)
+                {
+                    fmt = TILESPMV_FMT_HYB;
+                    width = hybwidth;
+                    slots = spill + hybwidth * rowlen;
+                    nd = spill;
+                }
+            }
         }
     }
     Format[t] = (char)fmt;
@@ -272,6 +304,9 @@ enum OffsetKind
     OFF_DNSROWPTR,
     OFF_DNSCOLPTR,
     OFF_NEWCOO,
+    OFF_HYB,
+    OFF_HYBCOO,
+    OFF_HYBIDX,
     OFF_ZERO
 };
 struct OffsetIn
@@ -295,8 +330,15 @@ struct OffsetIn
         case OFF_CSRPTR:
             return f == TILESPMV_FMT_CSR ? (tile_br[i] == tilem - 1 ? rowA - (tilem - 1) * TS : TS) : 0;
         case OFF_COO:
-        case OFF_NEWCOO:
             return f == TILESPMV_FMT_COO ? slots[i] : 0;
+        case OFF_NEWCOO: // COO tiles whole, HYB tiles their spilled entries (:316)
+            return f == TILESPMV_FMT_COO ? slots[i] : f == TILESPMV_FMT_HYB ? nd[i] : 0;
+        case OFF_HYB:
+            return f == TILESPMV_FMT_HYB ? slots[i] : 0;
+        case OFF_HYBCOO:
+            return f == TILESPMV_FMT_HYB ? nd[i] : 0;
+        case OFF_HYBIDX: // bytes of the tile in hybIdx: nibble bytes of the ELL part + one byte per spilled entry (:994-1004)
+            return f == TILESPMV_FMT_HYB ? (slots[i] - nd[i] + 1) / 2 + nd[i] : 0;
         case OFF_ELL:
             return f == TILESPMV_FMT_ELL ? slots[i] : 0;
         case OFF_DNS:
@@ -349,9 +391,10 @@ struct ScatterArgs
     const int *tile_nnz, *tile_br;
     const char *Format;
     const unsigned char *rowstart;
-    const int *csr_offset, *coo_offset, *ell_offset, *dns_offset, *dnsrow_offset, *dnscol_offset, *dnscolptr;
-    T *Blockcsr_Val, *Blockcoo_Val, *Blockell_Val, *Blockdense_Val, *Blockdenserow_Val, *Blockdensecol_Val;
-    unsigned char *csr_lc, *ell_lc, *coo_idx;
+    const int *csr_offset, *coo_offset, *ell_offset, *hyb_offset, *dns_offset, *dnsrow_offset, *dnscol_offset, *dnscolptr;
+    const char *tilewidth;
+    T *Blockcsr_Val, *Blockcoo_Val, *Blockell_Val, *Blockhyb_Val, *Blockdense_Val, *Blockdenserow_Val, *Blockdensecol_Val;
+    unsigned char *csr_lc, *ell_lc, *hyb_lc, *coo_idx;
     char *densecolid;
     unsigned char *sideflag;
 };
@@ -396,6 +439,33 @@ __global__ void __launch_bounds__(CV_THREADS) scatter_kernel(ScatterArgs<T> a)
         int o = a.ell_offset[t] + kr * rowlen + r;
         a.Blockell_Val[o] = v;
         a.ell_lc[o] = (unsigned char)lc;
+        break;
+    }
+    case TILESPMV_FMT_HYB:
+    {
+        // ELL part slot-major like format 2; entries past the width follow it in row order (:519-546) and
+        // are ALSO handed to the side matrix (new_coocount, :538-545)
+        const int w = (int)(unsigned char)a.tilewidth[t];
+        const int base = a.hyb_offset[t];
+        if (kr < w)
+        {
+            a.Blockhyb_Val[base + kr * rowlen + r] = v;
+            a.hyb_lc[base + kr * rowlen + r] = (unsigned char)lc;
+        }
+        else
+        {
+            const unsigned char *rs = a.rowstart + (size_t)t * TS;
+            int before = 0;
+            for (int q = 0; q < r; q++)
+            {
+                const int len = (int)rs[q + 1] - (int)rs[q];
+                before += len > w ? len - w : 0;
+            }
+            const int o = base + w * rowlen + before + (kr - w);
+            a.Blockhyb_Val[o] = v;
+            a.hyb_lc[o] = (unsigned char)((r << 4) + lc);
+            a.sideflag[j] = 1;
+        }
         break;
     }
     case TILESPMV_FMT_DENSE:
@@ -460,6 +530,31 @@ __global__ void __launch_bounds__(CV_THREADS)
     unsigned hi = idx[2 * b];
     unsigned lo = 2 * b + 1 < len ? idx[2 * b + 1] : 0u;
     out[b] = (unsigned char)((hi << 4) + lo);
+}
+
+// HYB tiles pack their indices tile by tile (csr2tile.h:984-1008): ceil(w*rowlen/2) nibble bytes of the ELL part
+// (parity by position INSIDE the tile), then one (row << 4) + col byte per spilled entry.  One thread per tile.
+__global__ void __launch_bounds__(128)
+    pack_hyb_kernel(int T, const char *__restrict__ Format, const int *__restrict__ hyb_offset,
+                    const int *__restrict__ hyb_coocount, const int *__restrict__ hyb_idxoff,
+                    const unsigned char *__restrict__ lc, unsigned char *__restrict__ out)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T || Format[t] != TILESPMV_FMT_HYB)
+        return;
+    const int base = hyb_offset[t];
+    const int spill = hyb_coocount[t + 1] - hyb_coocount[t];
+    const int ell = hyb_offset[t + 1] - base - spill;
+    unsigned char *o = out + hyb_idxoff[t];
+    for (int b = 0; 2 * b < ell; b++)
+    {
+        unsigned hi = lc[base + 2 * b];
+        unsigned lo = 2 * b + 1 < ell ? lc[base + 2 * b + 1] : 0u;
+        o[b] = (unsigned char)((hi << 4) + lo);
+    }
+    o += (ell + 1) / 2;
+    for (int i = 0; i < spill; i++)
+        o[i] = lc[base + ell + i];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -548,7 +643,7 @@ static int read_last_int(const DevBuf &b, int idx, int *out, cudaStream_t s)
 
 template <class T>
 int convert_csr_to_tiles(int rowA, int colA, const int *d_rowptr, const int *d_colidx, const T *d_val,
-                         tilespmv_dmat *M, cudaStream_t s)
+                         tilespmv_dmat *M, cudaStream_t s, bool enable_hyb)
 {
     if (rowA < 0 || colA < 0)
     {
@@ -635,7 +730,7 @@ int convert_csr_to_tiles(int rowA, int colA, const int *d_rowptr, const int *d_c
     if (NT)
         TSP_LAUNCH(classify_kernel, grid_for((size_t)NT, 128), 128, 0, s, NT, M->tile_nnz.as<int>(), tile_br.as<int>(),
                    M->tile_columnidx.as<int>(), rowstart.as<unsigned char>(), V, d_colidx, tilem, tilen, rowA, colA,
-                   M->Format.as<char>(), slots.as<int>(), M->tilewidth.as<char>(), nd.as<int>());
+                   enable_hyb ? (int)sizeof(T) : 0, M->Format.as<char>(), slots.as<int>(), M->tilewidth.as<char>(), nd.as<int>());
 
     // ---- 4. prefix offsets (NT+1 entries each, last = total), blknnznnz, format histogram ----
     TSP_TRY(M->blknnznnz.alloc((size_t)NT + 1, true, s));
@@ -643,15 +738,16 @@ int convert_csr_to_tiles(int rowA, int colA, const int *d_rowptr, const int *d_c
     TSP_TRY(hist.alloc(8 * sizeof(unsigned long long), true, s));
     TSP_LAUNCH(blknnznnz_kernel, grid_for((size_t)NT + 1, CV_THREADS), CV_THREADS, 0, s, slots.as<int>(), NT,
                M->blknnznnz.as<unsigned char>(), M->Format.as<char>(), hist.as<unsigned long long>());
+    DevBuf hyb_idxoff; // byte offset of every HYB tile inside hybIdx (conversion scratch)
     struct
     {
         DevBuf *buf;
         int kind;
     } offs[] = {{&M->blknnz, OFF_BLKNNZ},        {&M->csr_offset, OFF_CSR},         {&M->csrptr_offset, OFF_CSRPTR},
-                {&M->coo_offset, OFF_COO},       {&M->ell_offset, OFF_ELL},         {&M->hyb_offset, OFF_ZERO},
-                {&M->hyb_coocount, OFF_ZERO},    {&M->dns_offset, OFF_DNS},         {&M->dnsrow_offset, OFF_DNSROW},
-                {&M->dnscol_offset, OFF_DNSCOL}, {&M->dnsrowptr, OFF_DNSROWPTR},    {&M->dnscolptr, OFF_DNSCOLPTR},
-                {&M->new_coocount, OFF_NEWCOO}};
+                {&M->coo_offset, OFF_COO},       {&M->ell_offset, OFF_ELL},         {&M->hyb_offset, enable_hyb ? OFF_HYB : OFF_ZERO},
+                {&M->hyb_coocount, enable_hyb ? OFF_HYBCOO : OFF_ZERO},             {&M->dns_offset, OFF_DNS},
+                {&M->dnsrow_offset, OFF_DNSROW}, {&M->dnscol_offset, OFF_DNSCOL},   {&M->dnsrowptr, OFF_DNSROWPTR},
+                {&M->dnscolptr, OFF_DNSCOLPTR},  {&M->new_coocount, OFF_NEWCOO},    {&hyb_idxoff, enable_hyb ? OFF_HYBIDX : OFF_ZERO}};
     for (auto &o : offs)
     {
         TSP_TRY(o.buf->alloc((size_t)(NT + 1) * 4, true, s));
@@ -661,6 +757,7 @@ int convert_csr_to_tiles(int rowA, int colA, const int *d_rowptr, const int *d_c
         long long tot = 0;
         TSP_TRY(exclusive_scan(in, (size_t)NT + 1, static_cast<int *>(o.buf->p), ws, s, &tot)); // also guards int overflow
     }
+    int hyb_idx_bytes = 0;
     if (NT)
     {
         TSP_TRY(read_last_int(M->csr_offset, NT, &M->csrsize, s));
@@ -673,6 +770,14 @@ int convert_csr_to_tiles(int rowA, int colA, const int *d_rowptr, const int *d_c
         TSP_TRY(read_last_int(M->dnsrowptr, NT, &M->ndenserowid, s));
         TSP_TRY(read_last_int(M->dnscolptr, NT, &M->ndensecolid, s));
         TSP_TRY(read_last_int(M->new_coocount, NT, &M->coototal, s));
+        if (enable_hyb)
+        {
+            // hybsize / hybellsize / hybcoosize of the size pass (:752, :776-779)
+            TSP_TRY(read_last_int(M->hyb_offset, NT, &M->hybsize, s));
+            TSP_TRY(read_last_int(M->hyb_coocount, NT, &M->hybcoosize, s));
+            TSP_TRY(read_last_int(hyb_idxoff, NT, &hyb_idx_bytes, s));
+            M->hybellsize = M->hybsize - M->hybcoosize;
+        }
     }
     {
         unsigned long long h[8];
@@ -691,14 +796,19 @@ int convert_csr_to_tiles(int rowA, int colA, const int *d_rowptr, const int *d_c
     TSP_TRY(M->coo_compressed_Idx.alloc((size_t)M->coosize, true, s));
     TSP_TRY(M->Blockell_Val.alloc((size_t)M->ellsize * vs, true, s));
     TSP_TRY(M->ell_compressedIdx.alloc((size_t)(M->ellsize + 1) / 2, true, s));
-    TSP_TRY(M->Blockhyb_Val.alloc(0, true, s));
-    TSP_TRY(M->hybIdx.alloc(0, true, s));
+    // hybIdx: the reference sizes it ceil(hybellsize/2) + hybcoosize (:840-841) but fills it tile by tile with
+    // per-tile rounding (:994-1004), which is longer when several HYB tiles of the ragged last block row have an
+    // odd ELL part (a heap overrun upstream): allocate the larger of the two, export the reference's length
+    const size_t hyb_ref_bytes = ((size_t)M->hybellsize + 1) / 2 + (size_t)M->hybcoosize;
+    TSP_TRY(M->Blockhyb_Val.alloc((size_t)M->hybsize * vs, true, s));
+    TSP_TRY(M->hybIdx.alloc(std::max(hyb_ref_bytes, (size_t)hyb_idx_bytes), true, s));
     TSP_TRY(M->Blockdense_Val.alloc((size_t)M->dnssize * vs, true, s));
     TSP_TRY(M->Blockdenserow_Val.alloc((size_t)M->dnsrowsize * vs, true, s));
     TSP_TRY(M->denserowid.alloc((size_t)M->ndenserowid, true, s));
     TSP_TRY(M->Blockdensecol_Val.alloc((size_t)M->dnscolsize * vs, true, s));
     TSP_TRY(M->densecolid.alloc((size_t)M->ndensecolid, true, s));
-    DevBuf csr_lc, ell_lc, sideflag;
+    DevBuf csr_lc, ell_lc, hyb_lc, sideflag;
+    TSP_TRY(hyb_lc.alloc((size_t)M->hybsize, true, s));
     TSP_TRY(csr_lc.alloc((size_t)M->csrsize, true, s));
     TSP_TRY(ell_lc.alloc((size_t)M->ellsize, true, s));
     TSP_TRY(sideflag.alloc(n + 1, true, s));
@@ -720,6 +830,10 @@ int convert_csr_to_tiles(int rowA, int colA, const int *d_rowptr, const int *d_c
         a.csr_offset = M->csr_offset.as<int>();
         a.coo_offset = M->coo_offset.as<int>();
         a.ell_offset = M->ell_offset.as<int>();
+        a.hyb_offset = M->hyb_offset.as<int>();
+        a.tilewidth = M->tilewidth.as<char>();
+        a.Blockhyb_Val = M->Blockhyb_Val.as<T>();
+        a.hyb_lc = hyb_lc.as<unsigned char>();
         a.dns_offset = M->dns_offset.as<int>();
         a.dnsrow_offset = M->dnsrow_offset.as<int>();
         a.dnscol_offset = M->dnscol_offset.as<int>();
@@ -748,6 +862,9 @@ int convert_csr_to_tiles(int rowA, int colA, const int *d_rowptr, const int *d_c
     if (M->ellsize)
         TSP_LAUNCH(pack_nibbles_kernel, grid_for((size_t)(M->ellsize + 1) / 2, CV_THREADS), CV_THREADS, 0, s,
                    ell_lc.as<unsigned char>(), M->ellsize, M->ell_compressedIdx.as<unsigned char>());
+    if (M->hybsize)
+        TSP_LAUNCH(pack_hyb_kernel, grid_for((size_t)NT, 128), 128, 0, s, NT, M->Format.as<char>(), M->hyb_offset.as<int>(),
+                   M->hyb_coocount.as<int>(), hyb_idxoff.as<int>(), hyb_lc.as<unsigned char>(), M->hybIdx.as<unsigned char>());
 
     // ---- 7. side CSR: compaction of the COO-tile nonzeros in original CSR order ----
     TSP_TRY(M->deferredcoo_ptr.alloc((size_t)(rowA + 1) * 4, true, s));
@@ -809,7 +926,7 @@ int convert_csr_to_tiles(int rowA, int colA, const int *d_rowptr, const int *d_c
     return TILESPMV_OK;
 }
 
-template int convert_csr_to_tiles<double>(int, int, const int *, const int *, const double *, tilespmv_dmat *, cudaStream_t);
-template int convert_csr_to_tiles<float>(int, int, const int *, const int *, const float *, tilespmv_dmat *, cudaStream_t);
+template int convert_csr_to_tiles<double>(int, int, const int *, const int *, const double *, tilespmv_dmat *, cudaStream_t, bool);
+template int convert_csr_to_tiles<float>(int, int, const int *, const int *, const float *, tilespmv_dmat *, cudaStream_t, bool);
 
 } // namespace tsp

@@ -50,5 +50,5 @@ namespace tsp
 // convert.cu
 template <class T>
 int convert_csr_to_tiles(int rowA, int colA, const int *d_rowptr, const int *d_colidx, const T *d_val,
-                         tilespmv_dmat *out, cudaStream_t s);
+                         tilespmv_dmat *out, cudaStream_t s, bool enable_hyb = false);
 } // namespace tsp

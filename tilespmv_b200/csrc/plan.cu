@@ -24,7 +24,8 @@ enum TileCostKind
     TC_STREAM_TILES, // 1 for every tile that lives in the stream (everything but COO)
     TC_OTHER_TILES,  // 1 for CSR / Dense / DenseRow / DenseCol
     TC_SLOTROWS,     // ELL / HYB width
-    TC_OTHER_BYTES   // payload bytes of the non-ELL tiles
+    TC_OTHER_BYTES,  // payload bytes of the non-ELL tiles
+    TC_HYB_IDXBYTES  // bytes of a HYB tile in hybIdx: ceil(w * rowlen / 2) nibble bytes + one byte per spilled entry
 };
 struct TileCostIn
 {
@@ -35,6 +36,8 @@ struct TileCostIn
     int T;
     uint32_t vs;
     int kind;
+    const int *blknnz = nullptr; // TC_HYB_IDXBYTES only
+    int last_row_tile0 = 0, last_rowlen = TS;
     __device__ __forceinline__ int operator()(size_t i) const
     {
         if (i >= (size_t)T)
@@ -48,6 +51,14 @@ struct TileCostIn
             return fmt_is_other(f) ? 1 : 0;
         case TC_SLOTROWS:
             return fmt_is_ell(f) ? (int)(unsigned char)width[i] : 0;
+        case TC_HYB_IDXBYTES:
+        {
+            if (f != TILESPMV_FMT_HYB)
+                return 0;
+            const int rowlen = (int)i >= last_row_tile0 ? last_rowlen : TS;
+            const int ell = (int)(unsigned char)width[i] * rowlen;
+            return (ell + 1) / 2 + (blknnz[i + 1] - blknnz[i] - ell);
+        }
         default:
         {
             if (!fmt_is_other(f))
@@ -109,8 +120,11 @@ struct PackArgs
     int rowA, colA, tilem, tilen;
     const int *tile_columnidx, *tile_nnz;
     const char *Format, *tilewidth;
-    const int *csr_offset, *csrptr_offset, *ell_offset, *dns_offset, *dnsrow_offset, *dnscol_offset, *dnsrowptr,
-        *dnscolptr;
+    const int *csr_offset, *csrptr_offset, *ell_offset, *hyb_offset, *dns_offset, *dnsrow_offset, *dnscol_offset,
+        *dnsrowptr, *dnscolptr;
+    const int *hyb_idxoff; // byte offset of every tile in hybIdx (0 for non-HYB tiles' own bytes)
+    const T *Blockhyb_Val;
+    const unsigned char *hybIdx;
     const T *Blockcsr_Val, *Blockell_Val, *Blockdense_Val, *Blockdenserow_Val, *Blockdensecol_Val;
     const unsigned char *Blockcsr_Ptr, *csr_compressedIdx, *ell_compressedIdx;
     const char *denserowid, *densecolid;
@@ -124,13 +138,19 @@ __device__ __forceinline__ unsigned nib_global(const unsigned char *packed, int 
     return (pos & 1) ? (b & 15u) : (b >> 4);
 }
 
-// ELL tile -> w slot-rows of the row's ELL group (runs in one thread)
+// ELL / HYB tile -> w slot-rows of the row's ELL group (runs in one thread).  A HYB tile (format 3,
+// csr2tile.h:505-548) contributes its ELL part (w x rowlen slot-major values in Blockhyb_Val, nibbles packed
+// per tile in hybIdx, csr2tile.h:984-1008); its spilled entries are already in the side CSR (new_coocount).
 template <class T>
 __device__ void pack_ell_tile(const PackArgs<T> &a, int t, int br, unsigned xsel, T *vals, unsigned char *idx,
                               unsigned char *xs)
 {
     const int rowlen = br == a.tilem - 1 ? a.rowA - (a.tilem - 1) * TS : TS;
-    const int o = a.ell_offset[t];
+    const bool hyb = a.Format[t] == TILESPMV_FMT_HYB;
+    const int o = hyb ? a.hyb_offset[t] : a.ell_offset[t];
+    const T *src = hyb ? a.Blockhyb_Val : a.Blockell_Val;
+    const unsigned char *nib = hyb ? a.hybIdx + a.hyb_idxoff[t] : a.ell_compressedIdx;
+    const int nib0 = hyb ? 0 : o; // hybIdx nibbles are tile-local, ell_compressedIdx positions global
     const int w = (int)(unsigned char)a.tilewidth[t];
     for (int s = 0; s < w; s++)
     {
@@ -141,15 +161,13 @@ __device__ void pack_ell_tile(const PackArgs<T> &a, int t, int br, unsigned xsel
             T v0 = 0, v1 = 0;
             if (r < rowlen)
             {
-                int p = o + s * rowlen + r;
-                v0 = a.Blockell_Val[p];
-                n0 = nib_global(a.ell_compressedIdx, p);
+                v0 = src[o + s * rowlen + r];
+                n0 = nib_global(nib, nib0 + s * rowlen + r);
             }
             if (r + 1 < rowlen)
             {
-                int p = o + s * rowlen + r + 1;
-                v1 = a.Blockell_Val[p];
-                n1 = nib_global(a.ell_compressedIdx, p);
+                v1 = src[o + s * rowlen + r + 1];
+                n1 = nib_global(nib, nib0 + s * rowlen + r + 1);
             }
             vals[s * 16 + r] = v0;
             vals[s * 16 + r + 1] = v1;
@@ -508,18 +526,13 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
     uint32_t C = (uint32_t)P->chunk_bytes, X = (uint32_t)P->xstage_bytes; // 0 = chosen below from the row sizes
     ScanWorkspace ws;
 
-    if (dm->fmt_hist[TILESPMV_FMT_HYB] > 0)
-    {
-        set_error("plan: HYB tiles are not supported yet (the default selector never emits them, csr2tile.h:308-316)");
-        return TILESPMV_ERR_UNSUPPORTED;
-    }
-
     // ---- 1. per-tile prefix sums ----
-    DevBuf d_nc, d_oc, d_ws, d_ob;
+    DevBuf d_nc, d_oc, d_ws, d_ob, d_hi;
     TSP_TRY(d_nc.alloc((size_t)(T_ + 1) * sizeof(int), true, s));
     TSP_TRY(d_oc.alloc((size_t)(T_ + 1) * sizeof(int), true, s));
     TSP_TRY(d_ws.alloc((size_t)(T_ + 1) * sizeof(int), true, s));
     TSP_TRY(d_ob.alloc((size_t)(T_ + 1) * sizeof(long long), true, s));
+    TSP_TRY(d_hi.alloc((size_t)(T_ + 1) * sizeof(int), true, s));
     if (T_)
     {
         TileCostIn tc{dm->Format.as<char>(), dm->tile_nnz.as<int>(), dm->tilewidth.as<char>(),
@@ -531,6 +544,18 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
         TSP_TRY(exclusive_scan(tc, (size_t)T_ + 1, d_ws.as<int>(), ws, s, nullptr));
         tc.kind = TC_OTHER_BYTES;
         TSP_TRY(exclusive_scan(tc, (size_t)T_ + 1, d_ob.as<long long>(), ws, s, nullptr));
+        if (dm->fmt_hist[TILESPMV_FMT_HYB] > 0)
+        {
+            // byte offset of every HYB tile inside hybIdx (what the reference calls ptroffset2, tilespmv_cpu.h:196)
+            int last_tile0 = 0;
+            TSP_CUDA(cudaMemcpyAsync(&last_tile0, dm->tile_ptr.as<int>() + (tilem - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+            TSP_CUDA(cudaStreamSynchronize(s));
+            tc.kind = TC_HYB_IDXBYTES;
+            tc.blknnz = dm->blknnz.as<int>();
+            tc.last_row_tile0 = last_tile0;
+            tc.last_rowlen = rowA - (tilem - 1) * TS;
+            TSP_TRY(exclusive_scan(tc, (size_t)T_ + 1, d_hi.as<int>(), ws, s, nullptr));
+        }
     }
     TileScans sc{d_nc.as<int>(), d_oc.as<int>(), d_ws.as<int>(), d_ob.as<long long>()};
     DevBuf d_row_nt, d_row_no, d_row_nsr, d_row_ob, d_row_s0;
@@ -869,6 +894,10 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
         a.csr_offset = dm->csr_offset.as<int>();
         a.csrptr_offset = dm->csrptr_offset.as<int>();
         a.ell_offset = dm->ell_offset.as<int>();
+        a.hyb_offset = dm->hyb_offset.as<int>();
+        a.hyb_idxoff = d_hi.as<int>();
+        a.Blockhyb_Val = dm->Blockhyb_Val.as<T>();
+        a.hybIdx = dm->hybIdx.as<unsigned char>();
         a.dns_offset = dm->dns_offset.as<int>();
         a.dnsrow_offset = dm->dnsrow_offset.as<int>();
         a.dnscol_offset = dm->dnscol_offset.as<int>();
