@@ -250,6 +250,11 @@ void tilespmv_plan_destroy(tilespmv_plan *plan);
 int tilespmv_plan_spmv(tilespmv_plan *plan, const void *d_x, void *d_y, void *stream);
 /* y = A*x with HOST pointers: H2D of x, the SpMV, D2H of y, synchronous (the end-to-end path). */
 int tilespmv_plan_spmv_host(tilespmv_plan *plan, const void *x, void *y);
+/* y[i] = A*x[i] for nvec HOST vectors (x[i] has colA entries, y[i] rowA; pinned memory for full overlap),
+ * pipelined over a ring of device buffers: the H2D copy of vector i+1, the SpMV of vector i and the D2H copy of
+ * vector i-1 run concurrently on three streams.  Synchronous: returns when every y[i] is complete.  The reference
+ * has no counterpart (call_tilespmv_cuda, tilespmv_cuda.h:794, re-uploads the whole matrix for every call). */
+int tilespmv_plan_spmv_host_batch(tilespmv_plan *plan, int nvec, const void *const *x, void *const *y);
 
 /*
  * Multi-GPU repeated SpMV (row-block sharding, x replicated): after computing its rows the

@@ -142,6 +142,29 @@ def test_upload_of_a_reference_built_tile_matrix():
     ora.tile_destroy(Mo)
 
 
+def test_host_batch_pipeline_equals_single_calls():
+    """tilespmv_plan_spmv_host_batch (3-stream pipeline over a ring of device buffers) gives bit-identical
+    results to one tilespmv_plan_spmv_host call per vector, for more vectors than ring slots, pinned or not."""
+    import torch
+    m, n, rp, ci, v = CASES["rmat_12"]()  # has rows cut across chunks: the shared scratch must not race
+    dm = api.DeviceTileMatrix.from_csr(m, n, rp, ci, v)
+    plan = api.Plan(dm, chunk_bytes=2560, xstage_bytes=256)
+    assert plan.info().split_rows > 0
+    rng = np.random.default_rng(5)
+    nvec = 8
+    xs = [torch.from_numpy(rng.uniform(-1, 1, n)) for _ in range(nvec)]
+    want = [plan.spmv_host(x.numpy()) for x in xs]
+    for pinned in (True, False):
+        xin = [x.pin_memory() if pinned else x.clone() for x in xs]
+        ys = [torch.full((m,), float("nan"), dtype=torch.float64) for _ in range(nvec)]
+        if pinned:
+            ys = [y.pin_memory() for y in ys]
+        plan.spmv_host_batch([x.data_ptr() for x in xin], [y.data_ptr() for y in ys])
+        for y, w in zip(ys, want):
+            assert y.numpy().tobytes() == w.tobytes()
+    plan.spmv_host_batch([], [])
+
+
 def test_device_pointer_path_streams_and_linearity():
     """tilespmv_plan_spmv on torch device buffers and a non-default stream; A(ax+by) = aAx + bAy."""
     import torch

@@ -202,6 +202,15 @@ class Plan:
         check(_capi.load().tilespmv_plan_spmv_host(self.handle, _ptr(x), _ptr(y)), "tilespmv_plan_spmv_host")
         return y
 
+    def spmv_host_batch(self, x_ptrs, y_ptrs):
+        """y[i] = A*x[i] for lists of raw HOST pointers (ints; pinned memory for full overlap): H2D of vector
+        i+1, SpMV of vector i and D2H of vector i-1 run concurrently (tilespmv_plan_spmv_host_batch)."""
+        n = len(x_ptrs)
+        assert len(y_ptrs) == n
+        xa = (C.c_void_p * max(n, 1))(*[C.c_void_p(p) for p in x_ptrs])
+        ya = (C.c_void_p * max(n, 1))(*[C.c_void_p(p) for p in y_ptrs])
+        check(_capi.load().tilespmv_plan_spmv_host_batch(self.handle, n, xa, ya), "tilespmv_plan_spmv_host_batch")
+
     def time(self, d_x, d_y, warmup=3, iters=20, stream=0):
         ms = C.c_double(0)
         check(_capi.load().tilespmv_plan_time(self.handle, C.c_void_p(d_x), C.c_void_p(d_y), warmup, iters,

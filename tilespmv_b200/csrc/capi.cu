@@ -828,6 +828,61 @@ int tilespmv_plan_spmv_host(tilespmv_plan *plan, const void *x, void *y)
     return TILESPMV_OK;
 }
 
+int tilespmv_plan_spmv_host_batch(tilespmv_plan *plan, int nvec, const void *const *x, void *const *y)
+{
+    if (!plan || nvec < 0 || (nvec > 0 && (!x || !y)))
+    {
+        set_error("plan_spmv_host_batch: invalid argument");
+        return TILESPMV_ERR_INVALID;
+    }
+    constexpr int R = tilespmv_plan::HOST_RING;
+    const size_t xb = (size_t)plan->colA * (size_t)plan->precision, yb = (size_t)plan->rowA * (size_t)plan->precision;
+    if (!plan->s_in)
+    {
+        TSP_CUDA(cudaStreamCreateWithFlags(&plan->s_in, cudaStreamNonBlocking));
+        TSP_CUDA(cudaStreamCreateWithFlags(&plan->s_comp, cudaStreamNonBlocking));
+        TSP_CUDA(cudaStreamCreateWithFlags(&plan->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < R; i++)
+        {
+            TSP_CUDA(cudaEventCreateWithFlags(&plan->ev_in[i], cudaEventDisableTiming));
+            TSP_CUDA(cudaEventCreateWithFlags(&plan->ev_comp[i], cudaEventDisableTiming));
+            TSP_CUDA(cudaEventCreateWithFlags(&plan->ev_out[i], cudaEventDisableTiming));
+            TSP_TRY(plan->bx[i].alloc(xb, false));
+            TSP_TRY(plan->by[i].alloc(yb, true));
+        }
+    }
+    // vector i uses ring slot i % R.  H2D stream: x_i -> bx once the kernel that last read bx is done; kernel
+    // stream: SpMV once x_i has landed and the D2H that last read by is done; D2H stream: by -> y_i.  The two
+    // copy directions run concurrently (PCIe is full duplex) and both overlap the kernels.
+    for (int i = 0; i < nvec; i++)
+    {
+        const int b = i % R;
+        if (!x[i] && xb)
+        {
+            set_error("plan_spmv_host_batch: x[%d] is null", i);
+            return TILESPMV_ERR_INVALID;
+        }
+        if (i >= R)
+            TSP_CUDA(cudaStreamWaitEvent(plan->s_in, plan->ev_comp[b], 0));
+        if (xb)
+            TSP_CUDA(cudaMemcpyAsync(plan->bx[b].p, x[i], xb, cudaMemcpyHostToDevice, plan->s_in));
+        TSP_CUDA(cudaEventRecord(plan->ev_in[b], plan->s_in));
+        TSP_CUDA(cudaStreamWaitEvent(plan->s_comp, plan->ev_in[b], 0));
+        if (i >= R)
+            TSP_CUDA(cudaStreamWaitEvent(plan->s_comp, plan->ev_out[b], 0));
+        TSP_TRY(plan_launch(plan, plan->bx[b].p, plan->by[b].p, plan->s_comp));
+        TSP_CUDA(cudaEventRecord(plan->ev_comp[b], plan->s_comp));
+        TSP_CUDA(cudaStreamWaitEvent(plan->s_out, plan->ev_comp[b], 0));
+        if (yb && y[i])
+            TSP_CUDA(cudaMemcpyAsync(y[i], plan->by[b].p, yb, cudaMemcpyDeviceToHost, plan->s_out));
+        TSP_CUDA(cudaEventRecord(plan->ev_out[b], plan->s_out));
+    }
+    TSP_CUDA(cudaStreamSynchronize(plan->s_in));
+    TSP_CUDA(cudaStreamSynchronize(plan->s_comp));
+    TSP_CUDA(cudaStreamSynchronize(plan->s_out));
+    return TILESPMV_OK;
+}
+
 int tilespmv_plan_set_peers(tilespmv_plan *plan, int npeers, void *const *peer_x, int64_t row_offset)
 {
     if (!plan || npeers < 0 || npeers > TSP_MAX_PEERS || (npeers > 0 && !peer_x))

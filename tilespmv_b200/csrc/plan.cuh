@@ -43,10 +43,27 @@ struct tilespmv_plan
 
     // device staging for the host-pointer entry point
     tsp::DevBuf hx, hy;
+    // ... and for the pipelined batch entry point (tilespmv_plan_spmv_host_batch): a ring of x / y buffers,
+    // one stream per direction + one for the kernel, events that hand the buffers from stage to stage
+    static constexpr int HOST_RING = 3;
+    tsp::DevBuf bx[HOST_RING], by[HOST_RING];
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[HOST_RING] = {nullptr}, ev_comp[HOST_RING] = {nullptr}, ev_out[HOST_RING] = {nullptr};
+    ~tilespmv_plan()
+    {
+        for (int i = 0; i < HOST_RING; i++)
+            for (cudaEvent_t e : {ev_in[i], ev_comp[i], ev_out[i]})
+                if (e)
+                    cudaEventDestroy(e);
+        for (cudaStream_t st : {s_in, s_comp, s_out})
+            if (st)
+                cudaStreamDestroy(st);
+    }
 
     int64_t device_bytes() const
     {
-        return (int64_t)(stream.bytes + chunk_off.bytes + chunk_desc.bytes + head.bytes + scratch.bytes + split_tab.bytes + hx.bytes + hy.bytes);
+        return (int64_t)(stream.bytes + chunk_off.bytes + chunk_desc.bytes + head.bytes + scratch.bytes + split_tab.bytes + hx.bytes + hy.bytes + bx[0].bytes * HOST_RING +
+                         by[0].bytes * HOST_RING);
     }
 };
 
