@@ -237,8 +237,12 @@ typedef struct
     int ctas_per_sm;  /* persistent CTAs per SM (0 = default: 1, with as many warps as fit)  */
     int stages;       /* TMA pipeline depth per warp, 2..4 (0 = default: 2)                  */
     int max_warps;    /* cap on warps per CTA (0 = as many as shared memory holds, <= 20)    */
-    int reserved[3];
+    int flags;        /* TILESPMV_PLAN_* bits (0 = default)                                  */
+    int reserved[2];
 } tilespmv_plan_options;
+/* keep every CSR tile an individual tile of the packed stream instead of merging the CSR tiles of a block row
+ * into one jagged slot-row list (the default, faster; results agree to rounding) */
+#define TILESPMV_PLAN_NO_CSR_GROUPS 1
 
 /* Packs the tiles into the 16-byte-aligned per-chunk stream and builds the persistent,
  * byte-balanced chunk schedule.  opts may be NULL. */
@@ -277,6 +281,7 @@ typedef struct
     int grid, block, smem_bytes;
     int chunk_bytes, xstage_bytes;
     int64_t device_bytes;
+    int64_t csr_groups;        /* block rows whose CSR tiles were merged into one CSR group */
 } tilespmv_plan_info;
 int tilespmv_plan_get_info(const tilespmv_plan *plan, tilespmv_plan_info *info);
 

@@ -78,6 +78,19 @@ def test_convert_and_spmv_f32(name):
     check_matrix(CASES[name](), "f32")
 
 
+@pytest.mark.parametrize("name", ["seven_formats", "banded_8k", "banded_8k_real", "band_contig_8k", "rmat_12_real",
+                                  "ragged_band", "ragged_seven", "band_unsorted", "dense_48"])
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_csr_groups_and_individual_csr_tiles_agree(name, precision):
+    """The planner merges the CSR tiles of a block row into one CSR group (default); with
+    TILESPMV_PLAN_NO_CSR_GROUPS every CSR tile stays an individual tile.  Both must match the oracle."""
+    pg = check_matrix(CASES[name](), precision)
+    pi = check_matrix(CASES[name](), precision, plan_kwargs=dict(csr_groups=False))
+    assert pi.csr_groups == 0
+    if name.startswith("band"):
+        assert pg.csr_groups > 0
+
+
 @pytest.mark.parametrize("name", sorted(BIG_CASES))
 def test_convert_and_spmv_big(name):
     pi = check_matrix(BIG_CASES[name](), "f64")

@@ -918,6 +918,7 @@ int tilespmv_plan_get_info(const tilespmv_plan *plan, tilespmv_plan_info *info)
     info->chunk_bytes = plan->chunk_bytes;
     info->xstage_bytes = plan->xstage_bytes;
     info->device_bytes = plan->device_bytes();
+    info->csr_groups = plan->csr_groups;
     return TILESPMV_OK;
 }
 

@@ -25,6 +25,8 @@ enum TileCostKind
     TC_OTHER_TILES,  // 1 for CSR / Dense / DenseRow / DenseCol
     TC_SLOTROWS,     // ELL / HYB width
     TC_OTHER_BYTES,  // payload bytes of the non-ELL tiles
+    TC_NONCSR_TILES, // 1 for Dense / DenseRow / DenseCol
+    TC_NONCSR_BYTES, // payload bytes of Dense / DenseRow / DenseCol tiles
     TC_HYB_IDXBYTES  // bytes of a HYB tile in hybIdx: ceil(w * rowlen / 2) nibble bytes + one byte per spilled entry
 };
 struct TileCostIn
@@ -49,6 +51,8 @@ struct TileCostIn
             return f != TILESPMV_FMT_COO ? 1 : 0;
         case TC_OTHER_TILES:
             return fmt_is_other(f) ? 1 : 0;
+        case TC_NONCSR_TILES:
+            return fmt_is_other(f) && f != TILESPMV_FMT_CSR ? 1 : 0;
         case TC_SLOTROWS:
             return fmt_is_ell(f) ? (int)(unsigned char)width[i] : 0;
         case TC_HYB_IDXBYTES:
@@ -61,7 +65,7 @@ struct TileCostIn
         }
         default:
         {
-            if (!fmt_is_other(f))
+            if (!fmt_is_other(f) || (kind == TC_NONCSR_BYTES && f == TILESPMV_FMT_CSR))
                 return 0;
             const int nd = f == TILESPMV_FMT_DENSEROW ? dnsrowptr[i + 1] - dnsrowptr[i]
                                                       : (f == TILESPMV_FMT_DENSECOL ? dnscolptr[i + 1] - dnscolptr[i] : 0);
@@ -77,12 +81,15 @@ struct TileScans // all T+1 entries
     const int *oc;        // other tiles
     const int *ws;        // slot-rows
     const long long *ob;  // other payload bytes
+    const int *oc2;       // other tiles that are not CSR
+    const long long *ob2; // their payload bytes
 };
 
 __global__ void __launch_bounds__(PL_THREADS)
     row_summary_kernel(int tilem, int rowA, const int *__restrict__ tile_ptr, TileScans sc,
                        const int *__restrict__ side_ptr, int *__restrict__ row_nt, int *__restrict__ row_no,
-                       int *__restrict__ row_nsr, long long *__restrict__ row_ob, int *__restrict__ row_s0)
+                       int *__restrict__ row_nsr, long long *__restrict__ row_ob, int *__restrict__ row_s0,
+                       int *__restrict__ row_no2, long long *__restrict__ row_ob2)
 {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b > tilem)
@@ -96,7 +103,49 @@ __global__ void __launch_bounds__(PL_THREADS)
         row_no[b] = sc.oc[t1] - sc.oc[t0];
         row_nsr[b] = sc.ws[t1] - sc.ws[t0];
         row_ob[b] = sc.ob[t1] - sc.ob[t0];
+        row_no2[b] = sc.oc2[t1] - sc.oc2[t0];
+        row_ob2[b] = sc.ob2[t1] - sc.ob2[t0];
     }
+}
+
+// CSR tiles of every block row that is short enough for a CSR group (<= CSRGROUP_MAX_TILES stream tiles): number
+// of CSR tiles, their nonzeros, and the number of slot-rows = the longest local row summed over those tiles.
+__global__ void __launch_bounds__(PL_THREADS)
+    row_csr_summary_kernel(int tilem, int rowA, const int *__restrict__ tile_ptr, const char *__restrict__ Format,
+                           const int *__restrict__ tile_nnz, const int *__restrict__ csrptr_offset,
+                           const unsigned char *__restrict__ Blockcsr_Ptr, const int *__restrict__ row_nt,
+                           int *__restrict__ row_csr_cnt, int *__restrict__ row_csr_nnz, int *__restrict__ row_csr_nsrg)
+{
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= tilem)
+        return;
+    int cnt = 0, nnz_sum = 0, nsrg = 0;
+    if (row_nt[b] <= CSRGROUP_MAX_TILES)
+    {
+        const int rowlen = b == tilem - 1 ? rowA - (tilem - 1) * TS : TS;
+        int L[TS];
+#pragma unroll
+        for (int r = 0; r < TS; r++)
+            L[r] = 0;
+        for (int t = tile_ptr[b]; t < tile_ptr[b + 1]; t++)
+        {
+            if (Format[t] != TILESPMV_FMT_CSR)
+                continue;
+            const int nnz = tile_nnz[t + 1] - tile_nnz[t], po = csrptr_offset[t];
+            cnt++;
+            nnz_sum += nnz;
+#pragma unroll
+            for (int r = 0; r < TS; r++)
+                if (r < rowlen)
+                    L[r] += (r + 1 < rowlen ? (int)Blockcsr_Ptr[po + r + 1] : nnz) - (int)Blockcsr_Ptr[po + r];
+        }
+#pragma unroll
+        for (int r = 0; r < TS; r++)
+            nsrg = max(nsrg, L[r]);
+    }
+    row_csr_cnt[b] = cnt;
+    row_csr_nnz[b] = nnz_sum;
+    row_csr_nsrg[b] = nsrg;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -262,6 +311,78 @@ __device__ void pack_other_tile(const PackArgs<T> &a, int t, int br, unsigned xs
     *reinterpret_cast<uint2 *>(desc_out) = d;
 }
 
+// CSR group of one item (runs on the whole CTA): slot-row s holds the s-th entry of every local row that has one,
+// entries of a row counted across the item's CSR tiles in tile order (layout: stream.cuh)
+template <class T>
+__device__ void pack_csr_group(const PackArgs<T> &a, const PlanItem &it, unsigned xsel_base, unsigned char *desc_out,
+                               unsigned char *pay, int (*g_start)[CSRGROUP_MAX_TILES], int *g_len, unsigned *g_hdr)
+{
+    const int rowlen = it.rowlen;
+    const int nsrg = it.g_nsrg, n = it.g_n;
+    __syncthreads();
+    if (threadIdx.x < TS) // thread r: where local row r of every CSR tile starts in the row's merged list
+    {
+        const int r = threadIdx.x;
+        int L = 0, ord = 0;
+        for (int t = it.t0; t < it.t1; t++)
+        {
+            if (a.Format[t] != TILESPMV_FMT_CSR)
+                continue;
+            const int nnz = a.tile_nnz[t + 1] - a.tile_nnz[t], po = a.csrptr_offset[t];
+            g_start[r][ord++] = L;
+            if (r < rowlen)
+                L += (r + 1 < rowlen ? (int)a.Blockcsr_Ptr[po + r + 1] : nnz) - (int)a.Blockcsr_Ptr[po + r];
+        }
+        g_len[r] = L;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        unsigned off = 0;
+        for (int s = 0; s < nsrg; s++)
+        {
+            unsigned mask = 0;
+            for (int r = 0; r < TS; r++)
+                mask |= g_len[r] > s ? 1u << r : 0u;
+            g_hdr[s] = mask | (off << 16);
+            off += (unsigned)__popc(mask);
+        }
+        if (off != (unsigned)n || nsrg > CSRGROUP_MAX_SLOTROWS)
+            atomicExch(a.error_flag, 1);
+        uint2 d;
+        d.x = (uint32_t)TSP_FMT_CSRGROUP | (xsel_base << 8) | ((uint32_t)nsrg << 16);
+        d.y = (uint32_t)n;
+        *reinterpret_cast<uint2 *>(desc_out) = d;
+    }
+    __syncthreads();
+    uint32_t *hdr_out = reinterpret_cast<uint32_t *>(pay);
+    for (int s = threadIdx.x; s < nsrg; s += PACK_THREADS)
+        hdr_out[s] = g_hdr[s];
+    T *val_out = reinterpret_cast<T *>(pay + pad16(4u * (uint32_t)nsrg));
+    unsigned char *idx_out = pay + pad16(4u * (uint32_t)nsrg) + pad16((uint32_t)n * (uint32_t)sizeof(T));
+    int ord = 0;
+    for (int t = it.t0; t < it.t1; t++)
+    {
+        if (a.Format[t] != TILESPMV_FMT_CSR)
+            continue;
+        const int nnz = a.tile_nnz[t + 1] - a.tile_nnz[t], po = a.csrptr_offset[t], o = a.csr_offset[t];
+        const unsigned tsel = (unsigned)(a.sc.nc[t] - a.sc.nc[it.t0]); // ordinal among the item's stream tiles (< 16)
+        for (int k = threadIdx.x; k < nnz; k += PACK_THREADS)
+        {
+            int r = 0; // last row whose start is <= k
+            for (int q = 1; q < rowlen; q++)
+                if ((int)a.Blockcsr_Ptr[po + q] <= k)
+                    r = q;
+            const int s = g_start[r][ord] + (k - (int)a.Blockcsr_Ptr[po + r]);
+            const unsigned h = g_hdr[s];
+            const unsigned pos = (h >> 16) + (unsigned)__popc(h & 0xffffu & ((1u << r) - 1u));
+            val_out[pos] = a.Blockcsr_Val[o + k];
+            idx_out[pos] = (unsigned char)((tsel << 4) | nib_global(a.csr_compressedIdx, o + k));
+        }
+        ord++;
+    }
+}
+
 constexpr int PACK_ITEM_INTS = 6; // per item: tile base, other base, payload base, side base, sidehdr idx, nsr
 
 // x-staging lists of chunk cn (tile column of every stream tile, global column of every extracted
@@ -317,6 +438,8 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long 
     __shared__ int s_start[TS + 1];
     __shared__ unsigned s_flags, s_head_flags;
     __shared__ uint32_t s_own_nt, s_own_ns;
+    __shared__ int g_start[TS][CSRGROUP_MAX_TILES], g_len[TS];
+    __shared__ unsigned g_hdr[CSRGROUP_MAX_SLOTROWS];
     const long long c = blockIdx.x;
     if (c >= nchunks)
         return;
@@ -333,9 +456,11 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long 
         {
             const PlanItem it = a.items[i0 + k];
             const int nt = a.sc.nc[it.t1] - a.sc.nc[it.t0];
-            const int no = a.sc.oc[it.t1] - a.sc.oc[it.t0];
             const int nsr = a.sc.ws[it.t1] - a.sc.ws[it.t0];
-            const uint32_t ob = (uint32_t)(a.sc.ob[it.t1] - a.sc.ob[it.t0]);
+            // a grouped item replaces its CSR tiles by ONE descriptor + payload placed before the other tiles
+            const int no = it.g_n ? a.sc.oc2[it.t1] - a.sc.oc2[it.t0] + 1 : a.sc.oc[it.t1] - a.sc.oc[it.t0];
+            const uint32_t ob = it.g_n ? (uint32_t)(a.sc.ob2[it.t1] - a.sc.ob2[it.t0]) + csr_group_bytes((uint32_t)it.g_nsrg, (uint32_t)it.g_n, vs)
+                                       : (uint32_t)(a.sc.ob[it.t1] - a.sc.ob[it.t0]);
             const int ns = it.s1 - it.s0;
             int *sb = s_base + PACK_ITEM_INTS * k;
             sb[0] = (int)ntiles;
@@ -417,13 +542,21 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long 
                 const uint32_t so = (uint32_t)(a.sc.ws[t] - a.sc.ws[it.t0]);
                 pack_ell_tile<T>(a, t, it.br, xsel, ell_vals + so * 16u, ell_idx + so * 8u, ell_xsel + so);
             }
-            else
+            else if (it.g_n == 0)
             {
                 const uint32_t oi = (uint32_t)(sb[1] + (a.sc.oc[t] - a.sc.oc[it.t0]));
                 const uint32_t po = (uint32_t)(a.sc.ob[t] - a.sc.ob[it.t0]);
                 pack_other_tile<T>(a, t, it.br, xsel, out + hdr.off_odesc + 8u * oi, other_pay + po);
             }
+            else if (f != TILESPMV_FMT_CSR) // grouped item: the group comes first, then the non-CSR tiles
+            {
+                const uint32_t oi = (uint32_t)(sb[1] + 1 + (a.sc.oc2[t] - a.sc.oc2[it.t0]));
+                const uint32_t po = csr_group_bytes((uint32_t)it.g_nsrg, (uint32_t)it.g_n, vs) + (uint32_t)(a.sc.ob2[t] - a.sc.ob2[it.t0]);
+                pack_other_tile<T>(a, t, it.br, xsel, out + hdr.off_odesc + 8u * oi, other_pay + po);
+            }
         }
+        if (it.g_n) // uniform across the CTA
+            pack_csr_group<T>(a, it, (unsigned)sb[0], out + hdr.off_odesc + 8u * (uint32_t)sb[1], other_pay, g_start, g_len, g_hdr);
         const int ns = it.s1 - it.s0; // uniform across the CTA
         if (ns > 0)
         {
@@ -527,7 +660,9 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
     ScanWorkspace ws;
 
     // ---- 1. per-tile prefix sums ----
-    DevBuf d_nc, d_oc, d_ws, d_ob, d_hi;
+    DevBuf d_nc, d_oc, d_ws, d_ob, d_hi, d_oc2, d_ob2;
+    TSP_TRY(d_oc2.alloc((size_t)(T_ + 1) * sizeof(int), true, s));
+    TSP_TRY(d_ob2.alloc((size_t)(T_ + 1) * sizeof(long long), true, s));
     TSP_TRY(d_nc.alloc((size_t)(T_ + 1) * sizeof(int), true, s));
     TSP_TRY(d_oc.alloc((size_t)(T_ + 1) * sizeof(int), true, s));
     TSP_TRY(d_ws.alloc((size_t)(T_ + 1) * sizeof(int), true, s));
@@ -544,6 +679,10 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
         TSP_TRY(exclusive_scan(tc, (size_t)T_ + 1, d_ws.as<int>(), ws, s, nullptr));
         tc.kind = TC_OTHER_BYTES;
         TSP_TRY(exclusive_scan(tc, (size_t)T_ + 1, d_ob.as<long long>(), ws, s, nullptr));
+        tc.kind = TC_NONCSR_TILES;
+        TSP_TRY(exclusive_scan(tc, (size_t)T_ + 1, d_oc2.as<int>(), ws, s, nullptr));
+        tc.kind = TC_NONCSR_BYTES;
+        TSP_TRY(exclusive_scan(tc, (size_t)T_ + 1, d_ob2.as<long long>(), ws, s, nullptr));
         if (dm->fmt_hist[TILESPMV_FMT_HYB] > 0)
         {
             // byte offset of every HYB tile inside hybIdx (what the reference calls ptroffset2, tilespmv_cpu.h:196)
@@ -557,19 +696,41 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
             TSP_TRY(exclusive_scan(tc, (size_t)T_ + 1, d_hi.as<int>(), ws, s, nullptr));
         }
     }
-    TileScans sc{d_nc.as<int>(), d_oc.as<int>(), d_ws.as<int>(), d_ob.as<long long>()};
-    DevBuf d_row_nt, d_row_no, d_row_nsr, d_row_ob, d_row_s0;
+    TileScans sc{d_nc.as<int>(), d_oc.as<int>(), d_ws.as<int>(), d_ob.as<long long>(), d_oc2.as<int>(), d_ob2.as<long long>()};
+    DevBuf d_row_nt, d_row_no, d_row_nsr, d_row_ob, d_row_s0, d_row_no2, d_row_ob2, d_row_cc, d_row_cn, d_row_cs;
+    const bool use_groups = !(P->flags & TILESPMV_PLAN_NO_CSR_GROUPS) && dm->fmt_hist[TILESPMV_FMT_CSR] > 0;
     const size_t nb1 = (size_t)tilem + 1;
     TSP_TRY(d_row_nt.alloc(nb1 * sizeof(int), true, s));
     TSP_TRY(d_row_no.alloc(nb1 * sizeof(int), true, s));
     TSP_TRY(d_row_nsr.alloc(nb1 * sizeof(int), true, s));
     TSP_TRY(d_row_ob.alloc(nb1 * sizeof(long long), true, s));
     TSP_TRY(d_row_s0.alloc(nb1 * sizeof(int), true, s));
+    TSP_TRY(d_row_no2.alloc(nb1 * sizeof(int), true, s));
+    TSP_TRY(d_row_ob2.alloc(nb1 * sizeof(long long), true, s));
     TSP_LAUNCH(row_summary_kernel, grid_for(nb1, PL_THREADS), PL_THREADS, 0, s, tilem, rowA, dm->tile_ptr.as<int>(), sc,
                dm->deferredcoo_ptr.as<int>(), d_row_nt.as<int>(), d_row_no.as<int>(), d_row_nsr.as<int>(),
-               d_row_ob.as<long long>(), d_row_s0.as<int>());
-    std::vector<long long> row_ob(nb1);
-    std::vector<int> row_nt(nb1), row_no(nb1), row_nsr(nb1), row_s0(nb1), tile_ptr(nb1);
+               d_row_ob.as<long long>(), d_row_s0.as<int>(), d_row_no2.as<int>(), d_row_ob2.as<long long>());
+    std::vector<long long> row_ob(nb1), row_ob2(nb1);
+    std::vector<int> row_nt(nb1), row_no(nb1), row_nsr(nb1), row_s0(nb1), tile_ptr(nb1), row_no2(nb1);
+    std::vector<int> row_cc, row_cn, row_cs; // CSR tiles / their nonzeros / slot-rows of a would-be CSR group
+    if (use_groups && tilem > 0)
+    {
+        TSP_TRY(d_row_cc.alloc((size_t)tilem * sizeof(int), true, s));
+        TSP_TRY(d_row_cn.alloc((size_t)tilem * sizeof(int), true, s));
+        TSP_TRY(d_row_cs.alloc((size_t)tilem * sizeof(int), true, s));
+        TSP_LAUNCH(row_csr_summary_kernel, grid_for((size_t)tilem, PL_THREADS), PL_THREADS, 0, s, tilem, rowA,
+                   dm->tile_ptr.as<int>(), dm->Format.as<char>(), dm->tile_nnz.as<int>(), dm->csrptr_offset.as<int>(),
+                   dm->Blockcsr_Ptr.as<unsigned char>(), d_row_nt.as<int>(), d_row_cc.as<int>(), d_row_cn.as<int>(),
+                   d_row_cs.as<int>());
+        row_cc.resize(tilem);
+        row_cn.resize(tilem);
+        row_cs.resize(tilem);
+        TSP_CUDA(cudaMemcpyAsync(row_cc.data(), d_row_cc.p, (size_t)tilem * sizeof(int), cudaMemcpyDeviceToHost, s));
+        TSP_CUDA(cudaMemcpyAsync(row_cn.data(), d_row_cn.p, (size_t)tilem * sizeof(int), cudaMemcpyDeviceToHost, s));
+        TSP_CUDA(cudaMemcpyAsync(row_cs.data(), d_row_cs.p, (size_t)tilem * sizeof(int), cudaMemcpyDeviceToHost, s));
+    }
+    TSP_CUDA(cudaMemcpyAsync(row_ob2.data(), d_row_ob2.p, nb1 * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    TSP_CUDA(cudaMemcpyAsync(row_no2.data(), d_row_no2.p, nb1 * sizeof(int), cudaMemcpyDeviceToHost, s));
     TSP_CUDA(cudaMemcpyAsync(row_ob.data(), d_row_ob.p, nb1 * sizeof(long long), cudaMemcpyDeviceToHost, s));
     TSP_CUDA(cudaMemcpyAsync(row_nt.data(), d_row_nt.p, nb1 * sizeof(int), cudaMemcpyDeviceToHost, s));
     TSP_CUDA(cudaMemcpyAsync(row_no.data(), d_row_no.p, nb1 * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -583,6 +744,14 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
     //          row is 4 KB, a 37-per-row band 5.5 KB); larger stages mean fewer resident warps.
     //          Pick the smallest candidate that leaves at most ~5 % of the stream bytes (or what the
     //          largest candidate leaves, + 5 %) in rows that have to be cut.
+    // a block row whose CSR tiles can be merged into a CSR group (stream.cuh): payload / descriptor count with the group
+    auto groupable = [&](int b) {
+        return use_groups && row_cc[b] > 0 && row_nt[b] <= CSRGROUP_MAX_TILES && row_cs[b] <= CSRGROUP_MAX_SLOTROWS;
+    };
+    auto row_other_bytes = [&](int b) {
+        return groupable(b) ? row_ob2[b] + (long long)csr_group_bytes((uint32_t)row_cs[b], (uint32_t)row_cn[b], vs) : row_ob[b];
+    };
+    auto row_other_count = [&](int b) { return groupable(b) ? row_no2[b] + 1 : row_no[b]; };
     if (C == 0)
     {
         const uint32_t cand[5] = {4096u, 5120u, 6144u, 7168u, 8192u};
@@ -590,8 +759,8 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
         for (int b = 0; b < tilem; b++)
         {
             const int ns = row_s0[b + 1] - row_s0[b];
-            const double bytes = (double)CHUNK_OFF_ROWS + 16.0 + (double)pad16(8u * (uint32_t)row_no[b]) + (ns > 0 ? 48.0 : 0.0) +
-                                 (double)vs * ns + (double)ell_group_bytes((uint32_t)row_nsr[b], vs) + (double)row_ob[b] +
+            const double bytes = (double)CHUNK_OFF_ROWS + 16.0 + (double)pad16(8u * (uint32_t)row_other_count(b)) + (ns > 0 ? 48.0 : 0.0) +
+                                 (double)vs * ns + (double)ell_group_bytes((uint32_t)row_nsr[b], vs) + (double)row_other_bytes(b) +
                                  (double)list_bytes((uint32_t)row_nt[b], (uint32_t)ns);
             const double xb = (double)row_nt[b] * 16.0 * vs + (double)ns * vs;
             total += bytes;
@@ -640,11 +809,11 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
     {
         const int rowlen = b == tilem - 1 ? rowA - (tilem - 1) * TS : TS;
         const int ns = row_s0[b + 1] - row_s0[b];
-        const long long pay_ll = (long long)ell_group_bytes((uint32_t)row_nsr[b], vs) + row_ob[b];
+        const long long pay_ll = (long long)ell_group_bytes((uint32_t)row_nsr[b], vs) + row_other_bytes(b);
         ChunkAcc one;
         one.nrows = 1;
         one.ntiles = (uint32_t)row_nt[b];
-        one.nother = (uint32_t)row_no[b];
+        one.nother = (uint32_t)row_other_count(b);
         one.nside = (uint32_t)ns;
         one.nsiderows = ns > 0 ? 1 : 0;
         bool fits_alone = pay_ll < (long long)C && row_nt[b] <= 256 && row_nsr[b] < 60000 && ns < (int)C;
@@ -663,7 +832,14 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
                 trial = one;
             }
             acc = trial;
-            items.push_back(PlanItem{b, tile_ptr[b], tile_ptr[b + 1], row_s0[b], row_s0[b + 1], (uint32_t)b, rowlen});
+            PlanItem item{b, tile_ptr[b], tile_ptr[b + 1], row_s0[b], row_s0[b + 1], (uint32_t)b, rowlen};
+            if (groupable(b))
+            {
+                item.g_nsrg = row_cs[b];
+                item.g_n = row_cn[b];
+                P->csr_groups++;
+            }
+            items.push_back(item);
             continue;
         }
         // ---- long block row: cut into pieces, each piece is its own chunk ----
@@ -961,6 +1137,7 @@ int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tiles
     P->ctas_per_sm = opts ? opts->ctas_per_sm : 0;
     P->stages = opts ? opts->stages : 0;
     P->max_warps = opts ? opts->max_warps : 0;
+    P->flags = opts ? opts->flags : 0;
     if ((P->chunk_bytes != 0 && (P->chunk_bytes < 2560 || P->chunk_bytes > 32768 || (P->chunk_bytes & 127))) ||
         (P->xstage_bytes != 0 && (P->xstage_bytes < 16 * vs || P->xstage_bytes > 32768 || (P->xstage_bytes & 127))))
     {

@@ -32,6 +32,8 @@ struct tilespmv_plan
 
     // launch configuration of the persistent kernel
     int grid = 0, block = 0, smem = 0, ctas_per_sm = 0, sm_count = 0, stages = 0, max_warps = 0;
+    int flags = 0;            // TILESPMV_PLAN_*
+    int64_t csr_groups = 0;   // block rows whose CSR tiles were merged into a group
 
     // roofline accounting
     int64_t b_alg = 0, b_csr = 0;

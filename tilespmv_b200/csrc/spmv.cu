@@ -440,6 +440,44 @@ __device__ __forceinline__ void process_chunk(const unsigned char *st, uint32_t 
                 pay += pad16(16u + vbytes + pad8(((uint32_t)nnz + 1u) / 2u));
                 break;
             }
+            case TSP_FMT_CSRGROUP:
+            {
+                // all CSR tiles of the block row as one jagged list (stream.cuh): slot-row s = the s-th entry of
+                // every local row that has one.  Lane group g takes slot-rows g, g+4, ...; lane p finds the entries
+                // of rows 2p / 2p+1 from the slot-row's 16-bit row mask (popc of the bits below 2p) and its start
+                // offset.  Loads are unconditional (position <= n is always inside the payload, idx[n] = 0), only
+                // the FMAs are predicated; the trip count is warp-uniform.
+                const uint32_t nsrg = (uint32_t)w, n = d.y;
+                const uint32_t hdr_a = st_s + (uint32_t)(pay - st) + 4u * (uint32_t)g;
+                const uint32_t val_a = hdr_a - 4u * (uint32_t)g + pad16(4u * nsrg);
+                const uint32_t idx_a = val_a + pad16(n * VS);
+                const uint32_t xs_a = xb_s + ((d.x >> 8) & 0xffu) * (TS * VS);
+                const uint32_t sh = 2u * (uint32_t)p, below = (1u << sh) - 1u;
+#pragma unroll 1
+                for (uint32_t s0 = 0; s0 < nsrg; s0 += 8u)
+                {
+                    const uint32_t h0 = s0 + (uint32_t)g < nsrg ? lds_u32(hdr_a + 4u * s0) : 0u;
+                    const uint32_t h1 = s0 + 4u + (uint32_t)g < nsrg ? lds_u32(hdr_a + 4u * s0 + 16u) : 0u;
+                    const uint32_t q00 = (h0 >> 16) + (uint32_t)__popc(h0 & below), q01 = q00 + ((h0 >> sh) & 1u);
+                    const uint32_t q10 = (h1 >> 16) + (uint32_t)__popc(h1 & below), q11 = q10 + ((h1 >> sh) & 1u);
+                    const T v00 = SL<T>::ld(mad_u32(q00, VS, val_a)), v01 = SL<T>::ld(mad_u32(q01, VS, val_a));
+                    const T v10 = SL<T>::ld(mad_u32(q10, VS, val_a)), v11 = SL<T>::ld(mad_u32(q11, VS, val_a));
+                    const uint32_t i00 = lds_u8(idx_a + q00), i01 = lds_u8(idx_a + q01);
+                    const uint32_t i10 = lds_u8(idx_a + q10), i11 = lds_u8(idx_a + q11);
+                    const T x00 = SL<T>::ld(mad_u32(i00, VS, xs_a)), x01 = SL<T>::ld(mad_u32(i01, VS, xs_a));
+                    const T x10 = SL<T>::ld(mad_u32(i10, VS, xs_a)), x11 = SL<T>::ld(mad_u32(i11, VS, xs_a));
+                    if ((h0 >> sh) & 1u)
+                        a0 = fma_t<T>(v00, x00, a0);
+                    if ((h0 >> sh) & 2u)
+                        a1 = fma_t<T>(v01, x01, a1);
+                    if ((h1 >> sh) & 1u)
+                        a0 = fma_t<T>(v10, x10, a0);
+                    if ((h1 >> sh) & 2u)
+                        a1 = fma_t<T>(v11, x11, a1);
+                }
+                pay += csr_group_bytes(nsrg, n, VS);
+                break;
+            }
             case TILESPMV_FMT_DENSE:
             {
                 const V2 *dv = reinterpret_cast<const V2 *>(pay);

@@ -16,6 +16,12 @@
 //         val [nsr][16] T | nibbles [nsr][8] B | xsel [nsr] u8 (x segment of the slot-row), pad 16
 //     then the other tiles of the row in order, each padded to 16 B:
 //         CSR      : rowstart[16] u8 | val[nnz] T (pad 8) | nibbles ceil(nnz/2) (pad 8)
+//         CSR group: ALL CSR tiles of a block row with <= 16 stream tiles merged into one jagged list (stream-only
+//                    pseudo format TSP_FMT_CSRGROUP): slot-row s holds the s-th entry of every local row that has
+//                    one (counted across the row's CSR tiles in tile order), rows ascending, no padding:
+//                    hdr[nsrg] u32 {row mask | offset << 16} (pad 16) | val[n] T (pad 16) | idx[n+1] u8 (pad 16),
+//                    idx = (ordinal of the tile among the row's stream tiles) << 4 | local column = offset into the
+//                    row's window of staged x.  One branch-free loop per block row instead of one per tile.
 //         Dense    : val[16][16] T column-major (rows / columns padded with zeros)
 //         DenseRow : val[ndr][16] T row-major (padded); row ids as a 16-bit mask in the descriptor
 //         DenseCol : val[ndc][16] T slot-major | 16 column nibbles in one u64
@@ -72,6 +78,9 @@ constexpr uint32_t ROWF_HAS_SIDE = 1u;
 constexpr uint32_t SIDEHDR_BYTES = 40; // 17 x u16 used
 
 // ODesc as uint2: x = format | xsel << 8 | width << 16 ; y = aux (CSR nnz, DenseRow row mask)
+constexpr int TSP_FMT_CSRGROUP = 8;      // ODesc: xsel = first x segment of the row, width = slot-rows, aux = entries
+constexpr int CSRGROUP_MAX_TILES = 16;   // stream tiles of a block row that may use the group (4-bit tile ordinal)
+constexpr int CSRGROUP_MAX_SLOTROWS = 256;
 
 __host__ __device__ inline uint32_t pad8(uint32_t b) { return (b + 7u) & ~7u; }
 __host__ __device__ inline uint32_t pad16(uint32_t b) { return (b + 15u) & ~15u; }
@@ -95,6 +104,11 @@ __host__ __device__ inline uint32_t other_payload_bytes(int f, int nnz, int nd, 
     default:
         return 0u;
     }
+}
+// bytes of a CSR group with nsrg slot-rows and n entries
+__host__ __device__ inline uint32_t csr_group_bytes(uint32_t nsrg, uint32_t n, uint32_t vs)
+{
+    return pad16(4u * nsrg) + pad16(n * vs) + pad16(n + 1u);
 }
 // bytes of a row's ELL group with nsr slot-rows
 __host__ __device__ inline uint32_t ell_group_bytes(uint32_t nsr, uint32_t vs)
@@ -126,6 +140,7 @@ struct PlanItem
     int s0, s1;    // side-CSR entry range [s0, s1) (global positions in deferredcoo_*)
     uint32_t dest; // block row, or ROW_PARTIAL | slot
     int rowlen;
+    int g_nsrg = 0, g_n = 0; // CSR group of the item: slot-rows / entries (g_n = 0: CSR tiles stay individual tiles)
 };
 
 } // namespace tsp

@@ -1,6 +1,6 @@
 """A/B timing of plan configurations on ONE box, interleaved over several rounds.
 python tools/ab.py --grid 128 --configs "2:0,2:20,2:18,3:0" [--rounds 3] [--iters 100]
-config = stages:max_warps[:chunk_bytes[:xstage]]"""
+config = stages:max_warps[:chunk_bytes[:xstage[:nogroups]]] (nogroups = 1 keeps CSR tiles individual)"""
 import argparse
 import os
 import sys
@@ -35,7 +35,7 @@ def main():
     plans = []
     for c in a.configs.split(","):
         f = [int(t) for t in c.split(":")] + [0, 0, 0, 0]
-        p = api.Plan(dm, chunk_bytes=f[2], xstage_bytes=f[3], stages=f[0], max_warps=f[1])
+        p = api.Plan(dm, chunk_bytes=f[2], xstage_bytes=f[3], stages=f[0], max_warps=f[1], csr_groups=not f[4])
         plans.append((c, p))
     try:
         clk = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,power.draw", "--format=csv,noheader"],
@@ -51,7 +51,7 @@ def main():
     for c, p in plans:
         i = p.info()
         t = min(res[c])
-        print(f"  cfg {c:12s} block={i.block:4d} smem={i.smem_bytes:6d} chunks={i.nchunks} stream={i.stream_bytes} "
+        print(f"  cfg {c:12s} block={i.block:4d} smem={i.smem_bytes:6d} chunks={i.nchunks} groups={i.csr_groups} stream={i.stream_bytes} "
               f"us={' '.join(f'{u:.1f}' for u in res[c])}  best {t:.1f} us  {i.algorithmic_bytes / t / 1e3:.0f} GB/s(alg) "
               f"{2 * nnz / t / 1e3:.0f} GFLOP/s", flush=True)
 

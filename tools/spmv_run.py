@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
     ap.add_argument("--max-warps", type=int, default=0)
+    ap.add_argument("--no-csr-groups", action="store_true")
+    ap.add_argument("--hb", type=int, default=0)
     a = ap.parse_args()
     t0 = time.time()
     if a.workload == "lap3d27":
@@ -50,7 +52,7 @@ def main():
     torch.cuda.synchronize()
     t_conv = time.time() - t0
     t0 = time.time()
-    plan = api.Plan(dm, a.chunk_bytes, a.xstage_bytes, a.ctas_per_sm, a.stages, a.max_warps)
+    plan = api.Plan(dm, a.chunk_bytes, a.xstage_bytes, a.ctas_per_sm, a.stages, a.max_warps, csr_groups=not a.no_csr_groups)
     torch.cuda.synchronize()
     t_plan = time.time() - t0
     pi, di = plan.info(), dm.info()
@@ -60,7 +62,7 @@ def main():
     ms = plan.time(x.data_ptr(), y.data_ptr(), a.warmup, a.iters)
     nnz = int(rp[m])
     print(f"{a.workload} m={m} nnz={nnz} tiles={di.tilenum} fmt={list(di.tiles_by_format)} side={di.nnz_side} "
-          f"chunks={pi.nchunks} split={pi.split_rows} stream={pi.stream_bytes} B_alg={pi.algorithmic_bytes} "
+          f"chunks={pi.nchunks} split={pi.split_rows} groups={pi.csr_groups} stream={pi.stream_bytes} B_alg={pi.algorithmic_bytes} "
           f"grid={pi.grid} smem={pi.smem_bytes} | gen {t_gen:.2f}s conv {t_conv:.3f}s plan {t_plan:.3f}s | "
           f"{ms * 1e3:.1f} us/SpMV {2 * nnz / ms / 1e6:.1f} GFLOP/s {pi.algorithmic_bytes / ms / 1e6:.0f} GB/s(alg) "
           f"{pi.stream_bytes / ms / 1e6:.0f} GB/s(stream)", flush=True)
