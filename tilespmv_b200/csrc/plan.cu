@@ -347,11 +347,16 @@ __device__ void pack_csr_group(const PackArgs<T> &a, const PlanItem &it, unsigne
             g_hdr[s] = mask | (off << 16);
             off += (unsigned)__popc(mask);
         }
-        if (off != (unsigned)n || nsrg > CSRGROUP_MAX_SLOTROWS)
+        if (off != (unsigned)n || nsrg > CSRGROUP_MAX_SLOTROWS || n > 0xffff)
             atomicExch(a.error_flag, 1);
+        // leading slot-rows in which all 16 rows have an entry: the kernel runs them ELL-style (128-bit value
+        // loads, no mask arithmetic); entry (s, r) of that part sits at position 16 s + r
+        unsigned nfull = 0;
+        while (nfull < (unsigned)nsrg && (g_hdr[nfull] & 0xffffu) == 0xffffu)
+            nfull++;
         uint2 d;
         d.x = (uint32_t)TSP_FMT_CSRGROUP | (xsel_base << 8) | ((uint32_t)nsrg << 16);
-        d.y = (uint32_t)n;
+        d.y = (uint32_t)n | (nfull << 16);
         *reinterpret_cast<uint2 *>(desc_out) = d;
     }
     __syncthreads();

@@ -118,6 +118,12 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t a)
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a)
 {
     uint32_t v;
@@ -447,14 +453,62 @@ __device__ __forceinline__ void process_chunk(const unsigned char *st, uint32_t 
                 // of rows 2p / 2p+1 from the slot-row's 16-bit row mask (popc of the bits below 2p) and its start
                 // offset.  Loads are unconditional (position <= n is always inside the payload, idx[n] = 0), only
                 // the FMAs are predicated; the trip count is warp-uniform.
-                const uint32_t nsrg = (uint32_t)w, n = d.y;
+                const uint32_t nsrg = (uint32_t)w, n = d.y & 0xffffu, nfull = d.y >> 16;
                 const uint32_t hdr_a = st_s + (uint32_t)(pay - st) + 4u * (uint32_t)g;
                 const uint32_t val_a = hdr_a - 4u * (uint32_t)g + pad16(4u * nsrg);
                 const uint32_t idx_a = val_a + pad16(n * VS);
                 const uint32_t xs_a = xb_s + ((d.x >> 8) & 0xffu) * (TS * VS);
+                // ---- leading slot-rows with all 16 rows present: entry (s, r) is at position 16 s + r, so lane
+                //      (g, p) reads rows 2p / 2p+1 of slot-row s0 + g with one 128-bit load + one 16-bit index load
+                {
+                    uint32_t va = val_a + (uint32_t)lane * (2u * VS);
+                    uint32_t ia = idx_a + 2u * (uint32_t)lane;
+                    int left = (int)nfull;
+                    auto slot = [&](uint32_t j) {
+                        const V2 v = SL<T>::ld2(va + j * (64u * VS));
+                        const uint32_t u = lds_u16(ia + 64u * j);
+                        a0 = fma_t<T>(v.x, SL<T>::ld(mad_u32(u & 0xffu, VS, xs_a)), a0);
+                        a1 = fma_t<T>(v.y, SL<T>::ld(mad_u32(u >> 8, VS, xs_a)), a1);
+                    };
+                    auto slot_if = [&](uint32_t j, bool ok) { // predicated-off lanes read the CTA's zero block
+                        const V2 v = SL<T>::ld2(ok ? va + j * (64u * VS) : zero_s);
+                        const uint32_t u = lds_u16(ok ? ia + 64u * j : zero_s);
+                        a0 = fma_t<T>(v.x, SL<T>::ld(ok ? mad_u32(u & 0xffu, VS, xs_a) : zero_s), a0);
+                        a1 = fma_t<T>(v.y, SL<T>::ld(ok ? mad_u32(u >> 8, VS, xs_a) : zero_s), a1);
+                    };
+#pragma unroll 1
+                    for (; left >= 16; left -= 16)
+                    {
+                        slot(0);
+                        slot(1);
+                        slot(2);
+                        slot(3);
+                        va += 256u * VS;
+                        ia += 256u;
+                    }
+                    if (left >= 8)
+                    {
+                        slot(0);
+                        slot(1);
+                        va += 128u * VS;
+                        ia += 128u;
+                        left -= 8;
+                    }
+                    if (left > 0)
+                    {
+                        if (left > 4)
+                        {
+                            slot(0);
+                            slot_if(1, g + 4 < left);
+                        }
+                        else
+                            slot_if(0, g < left);
+                    }
+                }
+                // ---- ragged rest: positions from the slot-row's row mask and start offset
                 const uint32_t sh = 2u * (uint32_t)p, below = (1u << sh) - 1u;
 #pragma unroll 1
-                for (uint32_t s0 = 0; s0 < nsrg; s0 += 8u)
+                for (uint32_t s0 = nfull; s0 < nsrg; s0 += 8u)
                 {
                     const uint32_t h0 = s0 + (uint32_t)g < nsrg ? lds_u32(hdr_a + 4u * s0) : 0u;
                     const uint32_t h1 = s0 + 4u + (uint32_t)g < nsrg ? lds_u32(hdr_a + 4u * s0 + 16u) : 0u;
