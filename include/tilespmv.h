@@ -238,7 +238,11 @@ typedef struct
     int stages;       /* TMA pipeline depth per warp, 2..4 (0 = default: 2)                  */
     int max_warps;    /* cap on warps per CTA (0 = as many as shared memory holds, <= 20)    */
     int flags;        /* TILESPMV_PLAN_* bits (0 = default)                                  */
-    int reserved[2];
+    int xpanel_bytes; /* bytes of x per column panel of the extracted (side) matrix: 0 = automatic
+                         (panels only when x is far larger than L2 and side entries dominate),
+                         > 0 = that width, < 0 = never.  With panels one SpMV is one launch per
+                         panel, each gathering from an L2-resident window of x.                */
+    int reserved[1];
 } tilespmv_plan_options;
 /* keep every CSR tile an individual tile of the packed stream instead of merging the CSR tiles of a block row
  * into one jagged slot-row list (the default, faster; results agree to rounding) */
@@ -282,6 +286,7 @@ typedef struct
     int chunk_bytes, xstage_bytes;
     int64_t device_bytes;
     int64_t csr_groups;        /* block rows whose CSR tiles were merged into one CSR group */
+    int64_t xpanels;           /* column panels of the side matrix (1 = none; see xpanel_bytes) */
 } tilespmv_plan_info;
 int tilespmv_plan_get_info(const tilespmv_plan *plan, tilespmv_plan_info *info);
 

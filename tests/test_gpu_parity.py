@@ -91,6 +91,21 @@ def test_csr_groups_and_individual_csr_tiles_agree(name, precision):
         assert pg.csr_groups > 0
 
 
+@pytest.mark.parametrize("name,precision,panel", [("uniform_8k", "f64", 8192), ("uniform_8k", "f32", 4096), ("rmat_12", "f64", 4096),
+                                                  ("rmat_12_real", "f32", 1024), ("ragged_rmat", "f64", 2048),
+                                                  ("seven_formats", "f64", 128), ("lap2d_64", "f64", 4096),
+                                                  ("empty_rows", "f64", 128), ("band_contig_8k", "f64", 8192)])
+def test_x_panels_accumulating_sub_plans(name, precision, panel):
+    """xpanel_bytes forces the side matrix into column panels (one accumulating launch per panel, the layout
+    meant for x far larger than L2): same results, also with rows cut into pieces inside a panel."""
+    pi = check_matrix(CASES[name](), precision, plan_kwargs=dict(xpanel_bytes=panel))
+    if name not in ("band_contig_8k",):
+        assert pi.xpanels > 1 and pi.launches_per_spmv >= pi.xpanels - 1
+    pi = check_matrix(CASES[name](), precision, plan_kwargs=dict(xpanel_bytes=panel, chunk_bytes=2560, xstage_bytes=128))
+    pi = check_matrix(CASES[name](), precision, plan_kwargs=dict(xpanel_bytes=-1))
+    assert pi.xpanels == 1
+
+
 @pytest.mark.parametrize("name", sorted(BIG_CASES))
 def test_convert_and_spmv_big(name):
     pi = check_matrix(BIG_CASES[name](), "f64")

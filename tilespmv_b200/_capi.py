@@ -63,7 +63,7 @@ class DmatInfo(C.Structure):
 
 class PlanOptions(C.Structure):
     _fields_ = [("chunk_bytes", C.c_int), ("xstage_bytes", C.c_int), ("ctas_per_sm", C.c_int),
-                ("stages", C.c_int), ("max_warps", C.c_int), ("flags", C.c_int), ("reserved", C.c_int * 2)]
+                ("stages", C.c_int), ("max_warps", C.c_int), ("flags", C.c_int), ("xpanel_bytes", C.c_int), ("reserved", C.c_int * 1)]
 
 
 class PlanInfo(C.Structure):
@@ -71,7 +71,7 @@ class PlanInfo(C.Structure):
                 ("algorithmic_bytes", C.c_int64), ("csr_bytes", C.c_int64), ("split_rows", C.c_int64),
                 ("launches_per_spmv", C.c_int), ("grid", C.c_int), ("block", C.c_int),
                 ("smem_bytes", C.c_int), ("chunk_bytes", C.c_int), ("xstage_bytes", C.c_int),
-                ("device_bytes", C.c_int64), ("csr_groups", C.c_int64)]
+                ("device_bytes", C.c_int64), ("csr_groups", C.c_int64), ("xpanels", C.c_int64)]
 
 
 # every symbol include/tilespmv.h declares (checked by tests/test_capi_symbols.py)

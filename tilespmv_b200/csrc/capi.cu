@@ -911,7 +911,18 @@ int tilespmv_plan_get_info(const tilespmv_plan *plan, tilespmv_plan_info *info)
     info->algorithmic_bytes = plan->b_alg;
     info->csr_bytes = plan->b_csr;
     info->split_rows = plan->nsplit;
-    info->launches_per_spmv = plan->nchunks == 0 ? 0 : 1 + (plan->nsplit_small > 0 ? 1 : 0) + (plan->nsplit > plan->nsplit_small ? 1 : 0);
+    auto launches = [](const tilespmv_plan *q) {
+        return q->nchunks == 0 ? 0 : 1 + (q->nsplit_small > 0 ? 1 : 0) + (q->nsplit > q->nsplit_small ? 1 : 0);
+    };
+    info->launches_per_spmv = launches(plan);
+    for (const tilespmv_plan *q : plan->sub) // column-panel sub-plans: one more launch (+ fix-ups) each
+    {
+        info->nchunks += q->nchunks;
+        info->stream_bytes += q->stream_bytes;
+        info->split_rows += q->nsplit;
+        info->launches_per_spmv += launches(q);
+    }
+    info->xpanels = 1 + (int64_t)plan->sub.size();
     info->grid = plan->grid;
     info->block = plan->block;
     info->smem_bytes = plan->smem;

@@ -14,6 +14,7 @@ namespace tsp
 {
 
 constexpr int PL_THREADS = 256;
+constexpr double SPMV_SMEM_FIXED = 1024.0; // barriers + zero block of the SpMV kernel (spmv.cu), rounded up
 constexpr int PACK_THREADS = 128;
 
 // ---------------------------------------------------------------------------------------------
@@ -656,11 +657,20 @@ struct ChunkAcc
 };
 } // namespace
 
+// what one (sub-)plan is built from: the tiles of dm (or none) + a side matrix (dm's own, or one column panel of it)
+struct PlanSource
+{
+    bool tiles;
+    const int *tile_ptr; // dm->tile_ptr, or tilem+1 zeros when tiles is false
+    const int *side_ptr, *side_col;
+    const void *side_val;
+};
+
 template <class T>
-static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t s)
+static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv_plan *P, cudaStream_t s)
 {
     const uint32_t vs = (uint32_t)sizeof(T);
-    const int T_ = dm->tilenum, tilem = dm->tilem, rowA = dm->rowA;
+    const int T_ = src.tiles ? dm->tilenum : 0, tilem = dm->tilem, rowA = dm->rowA;
     uint32_t C = (uint32_t)P->chunk_bytes, X = (uint32_t)P->xstage_bytes; // 0 = chosen below from the row sizes
     ScanWorkspace ws;
 
@@ -703,7 +713,7 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
     }
     TileScans sc{d_nc.as<int>(), d_oc.as<int>(), d_ws.as<int>(), d_ob.as<long long>(), d_oc2.as<int>(), d_ob2.as<long long>()};
     DevBuf d_row_nt, d_row_no, d_row_nsr, d_row_ob, d_row_s0, d_row_no2, d_row_ob2, d_row_cc, d_row_cn, d_row_cs;
-    const bool use_groups = !(P->flags & TILESPMV_PLAN_NO_CSR_GROUPS) && dm->fmt_hist[TILESPMV_FMT_CSR] > 0;
+    const bool use_groups = !(P->flags & TILESPMV_PLAN_NO_CSR_GROUPS) && src.tiles && dm->fmt_hist[TILESPMV_FMT_CSR] > 0;
     const size_t nb1 = (size_t)tilem + 1;
     TSP_TRY(d_row_nt.alloc(nb1 * sizeof(int), true, s));
     TSP_TRY(d_row_no.alloc(nb1 * sizeof(int), true, s));
@@ -712,8 +722,8 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
     TSP_TRY(d_row_s0.alloc(nb1 * sizeof(int), true, s));
     TSP_TRY(d_row_no2.alloc(nb1 * sizeof(int), true, s));
     TSP_TRY(d_row_ob2.alloc(nb1 * sizeof(long long), true, s));
-    TSP_LAUNCH(row_summary_kernel, grid_for(nb1, PL_THREADS), PL_THREADS, 0, s, tilem, rowA, dm->tile_ptr.as<int>(), sc,
-               dm->deferredcoo_ptr.as<int>(), d_row_nt.as<int>(), d_row_no.as<int>(), d_row_nsr.as<int>(),
+    TSP_LAUNCH(row_summary_kernel, grid_for(nb1, PL_THREADS), PL_THREADS, 0, s, tilem, rowA, src.tile_ptr, sc,
+               src.side_ptr, d_row_nt.as<int>(), d_row_no.as<int>(), d_row_nsr.as<int>(),
                d_row_ob.as<long long>(), d_row_s0.as<int>(), d_row_no2.as<int>(), d_row_ob2.as<long long>());
     std::vector<long long> row_ob(nb1), row_ob2(nb1);
     std::vector<int> row_nt(nb1), row_no(nb1), row_nsr(nb1), row_s0(nb1), tile_ptr(nb1), row_no2(nb1);
@@ -741,7 +751,7 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
     TSP_CUDA(cudaMemcpyAsync(row_no.data(), d_row_no.p, nb1 * sizeof(int), cudaMemcpyDeviceToHost, s));
     TSP_CUDA(cudaMemcpyAsync(row_nsr.data(), d_row_nsr.p, nb1 * sizeof(int), cudaMemcpyDeviceToHost, s));
     TSP_CUDA(cudaMemcpyAsync(row_s0.data(), d_row_s0.p, nb1 * sizeof(int), cudaMemcpyDeviceToHost, s));
-    TSP_CUDA(cudaMemcpyAsync(tile_ptr.data(), dm->tile_ptr.p, nb1 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    TSP_CUDA(cudaMemcpyAsync(tile_ptr.data(), src.tile_ptr, nb1 * sizeof(int), cudaMemcpyDeviceToHost, s));
     TSP_CUDA(cudaStreamSynchronize(s));
 
     // ---- 1b. chunk size.  A block row that does not fit a chunk is cut into pieces whose partial sums
@@ -759,8 +769,11 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
     auto row_other_count = [&](int b) { return groupable(b) ? row_no2[b] + 1 : row_no[b]; };
     if (C == 0)
     {
-        const uint32_t cand[5] = {4096u, 5120u, 6144u, 7168u, 8192u};
-        double unfit[5] = {0, 0, 0, 0, 0}, total = 0;
+        // score of a candidate = resident warps per SM it leaves (2 stages + 2 x buffers per warp in 227 KB, at most
+        // 20) x (1 - half the share of stream bytes in rows that would have to be cut).  4 KB first: it wins ties,
+        // smaller stages only pay when rows are so uneven (power-law graphs) that warps matter more than cuts.
+        const uint32_t cand[7] = {4096u, 5120u, 6144u, 7168u, 8192u, 3072u, 2560u};
+        double unfit[7] = {0, 0, 0, 0, 0, 0, 0}, total = 0, total_x = 0;
         for (int b = 0; b < tilem; b++)
         {
             const int ns = row_s0[b + 1] - row_s0[b];
@@ -769,16 +782,26 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
                                  (double)list_bytes((uint32_t)row_nt[b], (uint32_t)ns);
             const double xb = (double)row_nt[b] * 16.0 * vs + (double)ns * vs;
             total += bytes;
-            for (int k = 0; k < 5; k++)
+            total_x += xb;
+            for (int k = 0; k < 7; k++)
                 if (bytes > cand[k] || xb > (X ? X : cand[k] * vs / 8u))
                     unfit[k] += bytes;
         }
         int pick = 0;
         if (total > 0)
         {
-            const double limit = std::max(0.05, unfit[4] / total + 0.05);
-            while (pick < 4 && unfit[pick] / total > limit)
-                pick++;
+            double best = -1.0;
+            for (int k = 0; k < 7; k++)
+            {
+                const double xk = X ? (double)X : std::min((double)(cand[k] * vs / 8u), total_x / total * cand[k] * 1.3 + 256.0);
+                const double warps = std::min(20.0, std::floor((227.0 * 1024.0 - SPMV_SMEM_FIXED) / (2.0 * cand[k] + 2.0 * xk)));
+                const double score = warps * (1.0 - 0.5 * unfit[k] / total);
+                if (score > best + 1e-9)
+                {
+                    best = score;
+                    pick = k;
+                }
+            }
         }
         C = cand[pick];
         P->chunk_bytes = (int)C;
@@ -814,6 +837,8 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
     {
         const int rowlen = b == tilem - 1 ? rowA - (tilem - 1) * TS : TS;
         const int ns = row_s0[b + 1] - row_s0[b];
+        if (!P->keep_all_rows && ns == 0 && row_nt[b] == 0)
+            continue; // an accumulating panel plan has nothing to add to this block row
         const long long pay_ll = (long long)ell_group_bytes((uint32_t)row_nsr[b], vs) + row_other_bytes(b);
         ChunkAcc one;
         one.nrows = 1;
@@ -1094,9 +1119,9 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
         a.ell_compressedIdx = dm->ell_compressedIdx.as<unsigned char>();
         a.denserowid = dm->denserowid.as<char>();
         a.densecolid = dm->densecolid.as<char>();
-        a.side_ptr = dm->deferredcoo_ptr.as<int>();
-        a.side_col = dm->deferredcoo_colidx.as<int>();
-        a.side_val = dm->deferredcoo_val.as<T>();
+        a.side_ptr = src.side_ptr;
+        a.side_col = src.side_col;
+        a.side_val = static_cast<const T *>(src.side_val);
         const size_t shm = (size_t)max_items * PACK_ITEM_INTS * sizeof(int);
         if (shm > 200 * 1024)
         {
@@ -1129,6 +1154,115 @@ static int plan_build_t(const tilespmv_dmat *dm, tilespmv_plan *P, cudaStream_t 
     return TILESPMV_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// x panels: the side matrix re-ordered panel-major (panel = column / panel_cols).  Rows are ascending by
+// column (csr2tile.h:952-960), so the entries of (row i, panel p) are a contiguous piece of row i.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lower_bound_col(const int *col, int lo, int hi, long long key)
+{
+    while (lo < hi)
+    {
+        const int mid = (lo + hi) >> 1;
+        if ((long long)col[mid] < key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+struct PanelCountIn // flattened [P][rowA + 1]: entries of (panel, row); the last slot of every panel is 0
+{
+    const int *side_ptr, *side_col;
+    int rowA, npanels;
+    long long panel_cols;
+    __device__ __forceinline__ int operator()(size_t k) const
+    {
+        const size_t stride = (size_t)rowA + 1;
+        if (k >= stride * (size_t)npanels)
+            return 0;
+        const int p = (int)(k / stride), i = (int)(k % stride);
+        if (i >= rowA)
+            return 0;
+        const int lo = side_ptr[i], hi = side_ptr[i + 1];
+        return lower_bound_col(side_col, lo, hi, (long long)(p + 1) * panel_cols) - lower_bound_col(side_col, lo, hi, (long long)p * panel_cols);
+    }
+};
+template <class T>
+__global__ void __launch_bounds__(PL_THREADS)
+    panel_scatter_kernel(int rowA, int npanels, long long panel_cols, const int *__restrict__ side_ptr,
+                         const int *__restrict__ side_col, const T *__restrict__ side_val, const int *__restrict__ ptr2,
+                         int *__restrict__ col2, T *__restrict__ val2)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rowA)
+        return;
+    const int lo = side_ptr[i], hi = side_ptr[i + 1];
+    int q = lo;
+    for (int p = 0; p < npanels && q < hi; p++)
+    {
+        const int e = lower_bound_col(side_col, q, hi, (long long)(p + 1) * panel_cols);
+        int dst = ptr2[(size_t)p * ((size_t)rowA + 1) + i];
+        for (; q < e; q++, dst++)
+        {
+            col2[dst] = side_col[q];
+            val2[dst] = side_val[q];
+        }
+    }
+}
+
+template <class T>
+static int plan_build_panels(const tilespmv_dmat *dm, tilespmv_plan *P, int npanels, long long panel_cols, cudaStream_t s)
+{
+    const int rowA = dm->rowA;
+    const size_t stride = (size_t)rowA + 1, flat = stride * (size_t)npanels;
+    ScanWorkspace ws;
+    DevBuf ptr2, col2, val2, zeros;
+    TSP_TRY(ptr2.alloc((flat + 1) * sizeof(int), false));
+    TSP_TRY(col2.alloc((size_t)dm->coototal * sizeof(int), false));
+    TSP_TRY(val2.alloc((size_t)dm->coototal * sizeof(T), false));
+    TSP_TRY(zeros.alloc(((size_t)dm->tilem + 1) * sizeof(int), true, s));
+    long long total = 0;
+    PanelCountIn in{dm->deferredcoo_ptr.as<int>(), dm->deferredcoo_colidx.as<int>(), rowA, npanels, panel_cols};
+    TSP_TRY(exclusive_scan(in, flat + 1, ptr2.as<int>(), ws, s, &total));
+    if (total != (long long)dm->coototal)
+    {
+        set_error("plan: x-panel split lost entries (%lld of %d)", total, dm->coototal);
+        return TILESPMV_ERR_CUDA;
+    }
+    TSP_LAUNCH((panel_scatter_kernel<T>), grid_for((size_t)rowA, PL_THREADS), PL_THREADS, 0, s, rowA, npanels, panel_cols,
+               dm->deferredcoo_ptr.as<int>(), dm->deferredcoo_colidx.as<int>(), dm->deferredcoo_val.as<T>(), ptr2.as<int>(),
+               col2.as<int>(), val2.as<T>());
+    const int user_chunk = P->chunk_bytes, user_xstage = P->xstage_bytes;
+    for (int p = 0; p < npanels; p++)
+    {
+        tilespmv_plan *Q = P;
+        if (p > 0)
+        {
+            Q = new (std::nothrow) tilespmv_plan();
+            if (!Q)
+                return TILESPMV_ERR_ALLOC;
+            P->sub.push_back(Q);
+            Q->precision = P->precision;
+            Q->rowA = P->rowA;
+            Q->colA = P->colA;
+            Q->tilem = P->tilem;
+            Q->ctas_per_sm = P->ctas_per_sm;
+            Q->stages = P->stages;
+            Q->max_warps = P->max_warps;
+            Q->flags = P->flags;
+            Q->chunk_bytes = user_chunk;
+            Q->xstage_bytes = user_xstage;
+            Q->accumulate = true;
+            Q->keep_all_rows = p == npanels - 1; // the last panel visits every row: it carries the fused peer stores
+        }
+        PlanSource src{p == 0, p == 0 ? dm->tile_ptr.as<int>() : zeros.as<int>(), ptr2.as<int>() + (size_t)p * stride, col2.as<int>(),
+                       val2.p};
+        TSP_TRY(plan_build_t<T>(dm, src, Q, s));
+    }
+    TSP_CUDA(cudaStreamSynchronize(s));
+    return TILESPMV_OK;
+}
+
 int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tilespmv_plan *P, cudaStream_t s)
 {
     P->precision = dm->precision;
@@ -1143,6 +1277,7 @@ int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tiles
     P->stages = opts ? opts->stages : 0;
     P->max_warps = opts ? opts->max_warps : 0;
     P->flags = opts ? opts->flags : 0;
+    P->xpanel_bytes = opts ? opts->xpanel_bytes : 0;
     if ((P->chunk_bytes != 0 && (P->chunk_bytes < 2560 || P->chunk_bytes > 32768 || (P->chunk_bytes & 127))) ||
         (P->xstage_bytes != 0 && (P->xstage_bytes < 16 * vs || P->xstage_bytes > 32768 || (P->xstage_bytes & 127))))
     {
@@ -1150,10 +1285,49 @@ int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tiles
                   16 * vs);
         return TILESPMV_ERR_INVALID;
     }
-    if (vs == 8)
-        TSP_TRY(plan_build_t<double>(dm, P, s));
+    // x panels (plan.cuh): automatic when x is larger than ~40 % of L2 and at least a quarter of the nonzeros are
+    // side entries (random gathers); xpanel_bytes > 0 forces that panel width, < 0 switches panels off
+    long long panel_bytes = 0;
+    if (P->xpanel_bytes > 0)
+        panel_bytes = P->xpanel_bytes;
+    else if (P->xpanel_bytes == 0 && dm->coototal > 0 && (int64_t)dm->coototal * 4 >= dm->nnz)
+    {
+        int dev = 0, l2 = 0;
+        TSP_CUDA(cudaGetDevice(&dev));
+        TSP_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
+        const long long budget = (long long)l2 * 2 / 5;
+        if ((long long)dm->colA * vs > 2 * budget)
+            panel_bytes = budget;
+    }
+    int npanels = 1;
+    long long panel_cols = 0;
+    if (panel_bytes > 0 && dm->coototal > 0)
+    {
+        panel_cols = std::max<long long>(TS, panel_bytes / vs / TS * TS);
+        long long np = ((long long)dm->colA + panel_cols - 1) / panel_cols;
+        if (np > 64) // bound the number of launches / y passes
+        {
+            np = 64;
+            panel_cols = (((long long)dm->colA + np - 1) / np + TS - 1) / TS * TS;
+            np = ((long long)dm->colA + panel_cols - 1) / panel_cols;
+        }
+        npanels = (int)std::max<long long>(np, 1);
+    }
+    if (npanels > 1)
+    {
+        if (vs == 8)
+            TSP_TRY(plan_build_panels<double>(dm, P, npanels, panel_cols, s));
+        else
+            TSP_TRY(plan_build_panels<float>(dm, P, npanels, panel_cols, s));
+    }
     else
-        TSP_TRY(plan_build_t<float>(dm, P, s));
+    {
+        PlanSource src{true, dm->tile_ptr.as<int>(), dm->deferredcoo_ptr.as<int>(), dm->deferredcoo_colidx.as<int>(), dm->deferredcoo_val.p};
+        if (vs == 8)
+            TSP_TRY(plan_build_t<double>(dm, src, P, s));
+        else
+            TSP_TRY(plan_build_t<float>(dm, src, P, s));
+    }
 
     // roofline accounting, SURVEY.md 8(d): every quantity from the (bit-exact) Tile_matrix
     const int64_t T_coo = dm->fmt_hist[TILESPMV_FMT_COO], T_csr = dm->fmt_hist[TILESPMV_FMT_CSR];

@@ -35,6 +35,15 @@ struct tilespmv_plan
     int flags = 0;            // TILESPMV_PLAN_*
     int64_t csr_groups = 0;   // block rows whose CSR tiles were merged into a group
 
+    // x panels: when x is much larger than L2 and most nonzeros are extracted (side) entries, the side matrix is
+    // cut into column panels of xpanel_bytes of x; this plan covers the tiles + panel 0 and writes y, sub[p-1]
+    // covers panel p and ACCUMULATES into y, launched in order, so that the random gathers of one launch stay
+    // inside an L2-resident window of x
+    int xpanel_bytes = 0;      // option: 0 = automatic, < 0 = off
+    bool accumulate = false;   // this (sub-)plan adds to y instead of writing it
+    bool keep_all_rows = true; // emit an item for every block row, also empty ones
+    std::vector<tilespmv_plan *> sub;
+
     // roofline accounting
     int64_t b_alg = 0, b_csr = 0;
 
@@ -53,6 +62,8 @@ struct tilespmv_plan
     cudaEvent_t ev_in[HOST_RING] = {nullptr}, ev_comp[HOST_RING] = {nullptr}, ev_out[HOST_RING] = {nullptr};
     ~tilespmv_plan()
     {
+        for (tilespmv_plan *q : sub)
+            delete q;
         for (int i = 0; i < HOST_RING; i++)
             for (cudaEvent_t e : {ev_in[i], ev_comp[i], ev_out[i]})
                 if (e)
@@ -64,7 +75,10 @@ struct tilespmv_plan
 
     int64_t device_bytes() const
     {
-        return (int64_t)(stream.bytes + chunk_off.bytes + chunk_desc.bytes + head.bytes + scratch.bytes + split_tab.bytes + hx.bytes + hy.bytes + bx[0].bytes * HOST_RING +
+        int64_t subs = 0;
+        for (const tilespmv_plan *q : sub)
+            subs += q->device_bytes();
+        return subs + (int64_t)(stream.bytes + chunk_off.bytes + chunk_desc.bytes + head.bytes + scratch.bytes + split_tab.bytes + hx.bytes + hy.bytes + bx[0].bytes * HOST_RING +
                          by[0].bytes * HOST_RING);
     }
 };

@@ -67,6 +67,20 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint3
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// the same with an L2 eviction-priority hint (the packed stream is read exactly once per SpMV: evict_first keeps it
+// from pushing the re-used x lines out of L2)
+__device__ __forceinline__ void tma_load_1d_hint(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase)
 {
     uint32_t done;
@@ -201,6 +215,7 @@ struct SpmvArgs
     int head_stride;
     int stage_stride, xstage_bytes;
     int npeers;
+    int accumulate; // y += A*x (column-panel sub-plans) instead of y = A*x
     long long row_offset;
     T *peers[TSP_MAX_PEERS];
 };
@@ -632,10 +647,21 @@ __device__ __forceinline__ void process_chunk(const unsigned char *st, uint32_t 
             {
                 const bool partial = (rec.x & ROW_PARTIAL) != 0;
                 const size_t row = (size_t)(rec.x & ~ROW_PARTIAL) * TS + r;
-                (partial ? a.scratch : a.y)[row] = acc;
-                if (!partial)
-                    for (int q = 0; q < a.npeers; q++) // fused all-gather: next x of every peer
-                        a.peers[q][a.row_offset + (long long)row] = acc;
+                if (a.accumulate && !partial && a.npeers == 0)
+                {
+                    // column-panel sub-plan: exactly one add per row and launch, launches are ordered by the stream,
+                    // so the sum is deterministic; the reduction is fire-and-forget (RED), no load to wait for
+                    atomicAdd(a.y + row, acc);
+                }
+                else
+                {
+                    if (a.accumulate && !partial)
+                        acc += a.y[row];
+                    (partial ? a.scratch : a.y)[row] = acc;
+                    if (!partial)
+                        for (int q = 0; q < a.npeers; q++) // fused all-gather: next x of every peer
+                            a.peers[q][a.row_offset + (long long)row] = acc;
+                }
             }
         }
     }
@@ -676,6 +702,9 @@ __global__ void __maxnreg__(MAXREG) tile_spmv_kernel(const SpmvArgs<T> a)
     __syncwarp();
 
     const uint32_t stage0 = smem_u32(wbase);
+    // the packed stream is read exactly once per SpMV: fetch it with L2 evict_first so that it does not push the
+    // re-used x lines out of L2 (uniform random 1 M x 6.25 M, x = 50 MB: 320 -> 184 us)
+    const uint64_t stream_policy = l2_policy_evict_first();
     // the first SPMV_STAGES chunks are fetched from the descriptor table; every later fetch takes
     // its descriptor from the header of the chunk whose stage it re-uses (no global load in the loop)
     if (lane == 0)
@@ -684,7 +713,7 @@ __global__ void __maxnreg__(MAXREG) tile_spmv_kernel(const SpmvArgs<T> a)
         {
             const uint2 d = a.chunk_desc[gw + (unsigned)k * nw];
             mbar_expect_tx(bar0 + 8u * k, d.y);
-            tma_load_1d(stage0 + (uint32_t)k * cb, a.stream + (size_t)d.x * 16u, d.y, bar0 + 8u * k);
+            tma_load_1d_hint(stage0 + (uint32_t)k * cb, a.stream + (size_t)d.x * 16u, d.y, bar0 + 8u * k, stream_policy);
         }
     }
 
@@ -728,7 +757,7 @@ __global__ void __maxnreg__(MAXREG) tile_spmv_kernel(const SpmvArgs<T> a)
             // the stage can be handed back to the async proxy (same hand-over as a consumer
             // release -> producer TMA in a warp-specialised pipeline)
             mbar_expect_tx(bar0 + 8u * st, issue.y);
-            tma_load_1d(st_s, a.stream + (size_t)issue.x * 16u, issue.y, bar0 + 8u * st);
+            tma_load_1d_hint(st_s, a.stream + (size_t)issue.x * 16u, issue.y, bar0 + 8u * st, stream_policy);
         }
         if (++st == SPMV_STAGES)
         {
@@ -757,6 +786,8 @@ __global__ void __launch_bounds__(128)
     for (int k = 0; k < e.z; k++)
         sum += scratch[(size_t)(e.y + k) * TS + r];
     const size_t row = (size_t)e.x * TS + r;
+    if (a.accumulate)
+        sum += y[row];
     y[row] = sum;
     for (int p = 0; p < npeers; p++)
         a.peers[p][row_offset + (long long)row] = sum;
@@ -792,6 +823,8 @@ __global__ void __launch_bounds__(256)
         for (int i = 0; i < 16; i++)
             sum += part[i][r];
         const size_t row = (size_t)e.x * TS + r;
+        if (a.accumulate)
+            sum += y[row];
         y[row] = sum;
         for (int p = 0; p < npeers; p++)
             a.peers[p][row_offset + (long long)row] = sum;
@@ -881,7 +914,7 @@ int spmv_configure(tilespmv_plan *P)
 }
 
 template <class T>
-static int plan_launch_t(tilespmv_plan *P, const T *x, T *y, cudaStream_t s)
+static int plan_launch_one(tilespmv_plan *P, const T *x, T *y, cudaStream_t s, int npeers, void *const *peers, int64_t row_offset)
 {
     if (P->nchunks == 0)
         return TILESPMV_OK;
@@ -897,10 +930,11 @@ static int plan_launch_t(tilespmv_plan *P, const T *x, T *y, cudaStream_t s)
     a.head_stride = P->head_stride;
     a.stage_stride = P->stage_stride;
     a.xstage_bytes = P->xstage_bytes;
-    a.npeers = P->npeers;
-    a.row_offset = P->row_offset;
+    a.npeers = npeers;
+    a.accumulate = P->accumulate ? 1 : 0;
+    a.row_offset = row_offset;
     for (int p = 0; p < TSP_MAX_PEERS; p++)
-        a.peers[p] = reinterpret_cast<T *>(P->peers[p]);
+        a.peers[p] = p < npeers ? reinterpret_cast<T *>(peers[p]) : nullptr;
     const int grid = P->grid; // fixed at plan time: the stream's lookahead lists depend on it
     {
         void *args[] = {(void *)&a};
@@ -914,12 +948,27 @@ static int plan_launch_t(tilespmv_plan *P, const T *x, T *y, cudaStream_t s)
     }
     if (P->nsplit > P->nsplit_small)
         TSP_LAUNCH((split_fixup_big_kernel<T>), (unsigned)(P->nsplit - P->nsplit_small), 256, 0, s,
-                   P->split_tab.as<int4>() + P->nsplit_small, P->scratch.as<T>(), y, P->npeers, (long long)P->row_offset, a);
+                   P->split_tab.as<int4>() + P->nsplit_small, P->scratch.as<T>(), y, npeers, (long long)row_offset, a);
     if (P->nsplit_small > 0)
     {
         const long long threads = P->nsplit_small * TS;
         TSP_LAUNCH((split_fixup_kernel<T>), grid_for((size_t)threads, 128), 128, 0, s, P->split_tab.as<int4>(), (long long)P->nsplit_small,
-                   P->scratch.as<T>(), y, P->npeers, (long long)P->row_offset, a);
+                   P->scratch.as<T>(), y, npeers, (long long)row_offset, a);
+    }
+    return TILESPMV_OK;
+}
+
+// the plan itself writes y; its column-panel sub-plans (plan.cuh) then accumulate in a fixed order.  The fused
+// peer stores ride on the LAST launch (which visits every row), when y is final.
+template <class T>
+static int plan_launch_t(tilespmv_plan *P, const T *x, T *y, cudaStream_t s)
+{
+    const bool alone = P->sub.empty();
+    TSP_TRY(plan_launch_one<T>(P, x, y, s, alone ? P->npeers : 0, P->peers, P->row_offset));
+    for (size_t i = 0; i < P->sub.size(); i++)
+    {
+        const bool last = i + 1 == P->sub.size();
+        TSP_TRY(plan_launch_one<T>(P->sub[i], x, y, s, last ? P->npeers : 0, P->peers, P->row_offset));
     }
     return TILESPMV_OK;
 }

@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--size", type=int, default=0)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--precision", default="f64")
+    ap.add_argument("--sim-world", type=int, default=0, help="on ONE GPU: time only the shard rank 0 of this many ranks would own (c5)")
+    ap.add_argument("--chunk-bytes", type=int, default=0)
+    ap.add_argument("--xpanel-bytes", type=int, default=0)
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -41,9 +44,12 @@ def main():
     t0 = time.time()
     if a.config == "c5":  # uniform random, 20 distinct columns per row: every rank generates its own rows
         N = a.size or 50_000_000
-        per = (N // 16 // world) * 16
-        rows = [(r * per, (r + 1) * per if r < world - 1 else N) for r in range(world)]
+        W = a.sim_world if (a.sim_world and world == 1) else world
+        per = (N // 16 // W) * 16
+        rows = [(r * per, (r + 1) * per if r < W - 1 else N) for r in range(W)]
         r0, r1 = rows[rank]
+        if W != world:
+            rows = [rows[0]]
         m, n, rp, ci, v = g.uniform_rows(N, r0, r1 - r0)
         name = f"uniform random {N}x{N}, 20 nnz/row (config 5)"
     else:  # banded: generated whole on every rank (counter-based RNG), cut by streamed bytes
@@ -58,7 +64,7 @@ def main():
     t_gen = time.time() - t0
     nnz_local = int(rp[r1 - r0])
     t0 = time.time()
-    sp = D.ShardedSpMV(rows, rank, n, rp, ci, v.astype(dt))
+    sp = D.ShardedSpMV(rows, rank, n, rp, ci, v.astype(dt), plan_kwargs=dict(chunk_bytes=a.chunk_bytes, xpanel_bytes=a.xpanel_bytes))
     torch.cuda.synchronize()
     t_setup = time.time() - t0
     del rp, ci, v
@@ -89,6 +95,7 @@ def main():
            "spmv_ms": ms_spmv, "spmv_gflops": 2.0 * nnz / ms_spmv / 1e6,
            "rank0": {"rows": sp.m_local, "nnz": nnz_local, "chunks": pi.nchunks, "split_rows": pi.split_rows,
                      "stream_bytes": pi.stream_bytes, "B_alg": pi.algorithmic_bytes, "block": pi.block,
+                     "xpanels": pi.xpanels, "launches_per_spmv": pi.launches_per_spmv, "chunk_bytes": pi.chunk_bytes,
                      "GBps_alg": pi.algorithmic_bytes / ms_spmv / 1e6},
            "gen_s": round(t_gen, 1), "convert_plan_s": round(t_setup, 1)}
     if world > 1:

@@ -28,6 +28,9 @@ def main():
     ap.add_argument("--max-warps", type=int, default=0)
     ap.add_argument("--no-csr-groups", action="store_true")
     ap.add_argument("--hb", type=int, default=0)
+    ap.add_argument("--rows", type=int, default=0)
+    ap.add_argument("--per-row", type=int, default=20)
+    ap.add_argument("--xpanel-bytes", type=int, default=0)
     a = ap.parse_args()
     t0 = time.time()
     if a.workload == "lap3d27":
@@ -41,7 +44,7 @@ def main():
     elif a.workload == "rmat":
         m, n, rp, ci, v = g.rmat(a.scale)
     elif a.workload == "uniform":
-        m, n, rp, ci, v = g.uniform(a.n)
+        m, n, rp, ci, v = g.uniform_rows(a.n, 0, a.rows or a.n, a.per_row)
     else:
         raise SystemExit("unknown workload")
     dt = np.float64 if a.precision == "f64" else np.float32
@@ -52,7 +55,7 @@ def main():
     torch.cuda.synchronize()
     t_conv = time.time() - t0
     t0 = time.time()
-    plan = api.Plan(dm, a.chunk_bytes, a.xstage_bytes, a.ctas_per_sm, a.stages, a.max_warps, csr_groups=not a.no_csr_groups)
+    plan = api.Plan(dm, a.chunk_bytes, a.xstage_bytes, a.ctas_per_sm, a.stages, a.max_warps, csr_groups=not a.no_csr_groups, xpanel_bytes=a.xpanel_bytes)
     torch.cuda.synchronize()
     t_plan = time.time() - t0
     pi, di = plan.info(), dm.info()
