@@ -27,7 +27,8 @@ def _worker(rank, world, port, case, K, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         m, n, rp, ci, v = getattr(g, case[0])(*case[1], val_mode=0)
-        sp = D.build_sharded(m, n, rp, ci, v)
+        # case[2]: plan options, e.g. x panels (column-panel sub-plans; the fused peer stores ride on the last launch)
+        sp = D.build_sharded(m, n, rp, ci, v, plan_kwargs=case[2] if len(case) > 2 else None)
         x0 = torch.from_numpy(np.random.default_rng(5).uniform(-1, 1, n)).cuda() / 64.0
         # single SpMV, no communication
         y = torch.empty(max(sp.m_local, 1), dtype=torch.float64, device="cuda")
@@ -45,7 +46,9 @@ def _worker(rank, world, port, case, K, q):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("case", [("banded", (65536,)), ("rmat", (13,)), ("lap3d27", (32,))], ids=lambda c: c[0])
+@pytest.mark.parametrize("case", [("banded", (65536,)), ("rmat", (13,)), ("lap3d27", (32,)),
+                                  ("rmat", (13,), dict(xpanel_bytes=8192)), ("uniform", (16384,), dict(xpanel_bytes=16384))],
+                         ids=lambda c: c[0] + ("_xpanels" if len(c) > 2 else ""))
 def test_sharded_spmv_and_repeated_spmv(case):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")

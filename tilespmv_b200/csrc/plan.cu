@@ -769,9 +769,9 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
     auto row_other_count = [&](int b) { return groupable(b) ? row_no2[b] + 1 : row_no[b]; };
     if (C == 0)
     {
-        // score of a candidate = resident warps per SM it leaves (2 stages + 2 x buffers per warp in 227 KB, at most
-        // 20) x (1 - half the share of stream bytes in rows that would have to be cut).  4 KB first: it wins ties,
-        // smaller stages only pay when rows are so uneven (power-law graphs) that warps matter more than cuts.
+        // Matrices made mostly of extracted entries: score of a candidate = resident warps per SM it leaves (2 stages +
+        // 2 x buffers per warp in 227 KB, at most 20) x (1 - half the share of stream bytes in rows that would have to
+        // be cut); 4 KB first: it wins ties.  Everything else: the smallest stage >= 4 KB that fits the rows.
         const uint32_t cand[7] = {4096u, 5120u, 6144u, 7168u, 8192u, 3072u, 2560u};
         double unfit[7] = {0, 0, 0, 0, 0, 0, 0}, total = 0, total_x = 0;
         for (int b = 0; b < tilem; b++)
@@ -788,8 +788,12 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
                     unfit[k] += bytes;
         }
         int pick = 0;
-        if (total > 0)
+        // mostly extracted (side) entries among the nonzeros THIS (sub-)plan handles?
+        const int64_t my_side = (int64_t)row_s0[tilem] - row_s0[0], my_tiled = src.tiles ? dm->nnz - dm->coototal : 0;
+        const bool gather_bound = my_side >= my_tiled;
+        if (total > 0 && gather_bound)
         {
+            // scattered x gathers are latency-bound: resident warps matter more than rows cut into pieces
             double best = -1.0;
             for (int k = 0; k < 7; k++)
             {
@@ -802,6 +806,14 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
                     pick = k;
                 }
             }
+        }
+        else if (total > 0)
+        {
+            // streaming tiles: the smallest stage >= 4 KB that leaves at most ~5 % of the stream bytes (or what the
+            // largest candidate leaves, + 5 %) in rows that have to be cut
+            const double limit = std::max(0.05, unfit[4] / total + 0.05);
+            while (pick < 4 && unfit[pick] / total > limit)
+                pick++;
         }
         C = cand[pick];
         P->chunk_bytes = (int)C;
