@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0)
     ap.add_argument("--per-row", type=int, default=20)
     ap.add_argument("--xpanel-bytes", type=int, default=0)
+    ap.add_argument("--check", action="store_true", help="compare y with torch's CSR SpMV (cuSPARSE) on the same device data")
     a = ap.parse_args()
     t0 = time.time()
     if a.workload == "lap3d27":
@@ -64,6 +65,23 @@ def main():
     y = torch.empty(m, dtype=tdt, device="cuda")
     ms = plan.time(x.data_ptr(), y.data_ptr(), a.warmup, a.iters)
     nnz = int(rp[m])
+    if a.check:
+        A = torch.sparse_csr_tensor(torch.from_numpy(rp).cuda().long(), torch.from_numpy(ci).cuda().long(),
+                                    torch.from_numpy(v).cuda(), size=(m, n))
+        y_ref = A @ x
+        scale = torch.sparse_csr_tensor(A.crow_indices(), A.col_indices(), A.values().abs(), size=(m, n)) @ x.abs()
+        tol = 1e-12 if a.precision == "f64" else 1e-5
+        bad = int(((y - y_ref).abs() > tol * scale.clamp_min(1e-30)).sum())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            A @ x
+        e0.record()
+        for _ in range(a.iters):
+            A @ x
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"check vs torch CSR SpMV: {bad} rows out of tolerance {tol} (relative to sum |a||x|); "
+              f"torch/cuSPARSE CSR SpMV on the same data: {e0.elapsed_time(e1) / a.iters * 1e3:.1f} us", flush=True)
     print(f"{a.workload} m={m} nnz={nnz} tiles={di.tilenum} fmt={list(di.tiles_by_format)} side={di.nnz_side} "
           f"chunks={pi.nchunks} split={pi.split_rows} groups={pi.csr_groups} stream={pi.stream_bytes} B_alg={pi.algorithmic_bytes} "
           f"grid={pi.grid} smem={pi.smem_bytes} | gen {t_gen:.2f}s conv {t_conv:.3f}s plan {t_plan:.3f}s | "
