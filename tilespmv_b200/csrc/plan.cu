@@ -791,6 +791,7 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
         // mostly extracted (side) entries among the nonzeros THIS (sub-)plan handles?
         const int64_t my_side = (int64_t)row_s0[tilem] - row_s0[0], my_tiled = src.tiles ? dm->nnz - dm->coototal : 0;
         const bool gather_bound = my_side >= my_tiled;
+        P->gather_bound = gather_bound;
         if (total > 0 && gather_bound)
         {
             // scattered x gathers are latency-bound: resident warps matter more than rows cut into pieces
@@ -798,7 +799,7 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
             for (int k = 0; k < 7; k++)
             {
                 const double xk = X ? (double)X : std::min((double)(cand[k] * vs / 8u), total_x / total * cand[k] * 1.3 + 256.0);
-                const double warps = std::min(20.0, std::floor((227.0 * 1024.0 - SPMV_SMEM_FIXED) / (2.0 * cand[k] + 2.0 * xk)));
+                const double warps = std::min(20.0, std::floor(((double)P->gather_smem_cap - SPMV_SMEM_FIXED) / (2.0 * cand[k] + 2.0 * xk)));
                 const double score = warps * (1.0 - 0.5 * unfit[k] / total);
                 if (score > best + 1e-9)
                 {
@@ -1262,6 +1263,7 @@ static int plan_build_panels(const tilespmv_dmat *dm, tilespmv_plan *P, int npan
             Q->stages = P->stages;
             Q->max_warps = P->max_warps;
             Q->flags = P->flags;
+            Q->gather_smem_cap = P->gather_smem_cap;
             Q->chunk_bytes = user_chunk;
             Q->xstage_bytes = user_xstage;
             Q->accumulate = true;
@@ -1290,6 +1292,8 @@ int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tiles
     P->max_warps = opts ? opts->max_warps : 0;
     P->flags = opts ? opts->flags : 0;
     P->xpanel_bytes = opts ? opts->xpanel_bytes : 0;
+    if (const char *e = getenv("TILESPMV_GATHER_SMEM_KB")) // experiments
+        P->gather_smem_cap = atoi(e) * 1024;
     if ((P->chunk_bytes != 0 && (P->chunk_bytes < 2560 || P->chunk_bytes > 32768 || (P->chunk_bytes & 127))) ||
         (P->xstage_bytes != 0 && (P->xstage_bytes < 16 * vs || P->xstage_bytes > 32768 || (P->xstage_bytes & 127))))
     {

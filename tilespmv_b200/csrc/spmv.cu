@@ -856,7 +856,9 @@ static int set_kernel_attrs(int stages, int warps, int smem_optin)
     // with different shared-memory footprints can coexist in one process
     const void *fn = kernel_for<T>(stages, warps);
     TSP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
-    TSP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    // prefer L1: the driver still has to provide the dynamic shared memory a launch asks for, so streaming plans
+    // (221 KB) get the 228 KB carve-out as before, while gather-bound plans (<= gather_smem_cap) leave >= 92 KB of L1
+    TSP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
     return TILESPMV_OK;
 }
 
@@ -877,7 +879,9 @@ int spmv_configure(tilespmv_plan *P)
         P->stages = 2;
     if (P->ctas_per_sm > 8)
         P->ctas_per_sm = 8;
-    const size_t budget = ((size_t)smem_optin + 1024) / P->ctas_per_sm - 1024; // 1 KB per CTA is reserved
+    size_t budget = ((size_t)smem_optin + 1024) / P->ctas_per_sm - 1024; // 1 KB per CTA is reserved
+    if (P->gather_bound && P->max_warps <= 0 && budget > (size_t)P->gather_smem_cap)
+        budget = (size_t)P->gather_smem_cap; // leave the rest of the SM's 256 KB to L1 (plan.cuh)
     const size_t per_warp = warp_smem_bytes(P);
     if (budget < SPMV_BAR_BYTES + per_warp)
     {
