@@ -1301,7 +1301,7 @@ int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tiles
                   16 * vs);
         return TILESPMV_ERR_INVALID;
     }
-    // x panels (plan.cuh): automatic when x is larger than ~40 % of L2 and at least a quarter of the nonzeros are
+    // x panels (plan.cuh): automatic when x is larger than L2 (panels of half of L2) and at least a quarter of the nonzeros are
     // side entries (random gathers); xpanel_bytes > 0 forces that panel width, < 0 switches panels off
     long long panel_bytes = 0;
     if (P->xpanel_bytes > 0)
@@ -1311,7 +1311,7 @@ int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tiles
         int dev = 0, l2 = 0;
         TSP_CUDA(cudaGetDevice(&dev));
         TSP_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
-        const long long budget = (long long)l2 * 2 / 5;
+        const long long budget = (long long)l2 / 2; // config-5 shard: 33 MB panels 1.32 ms, 50 MB 1.08, 67 MB 1.06, 100 MB 1.25
         if ((long long)dm->colA * vs > 2 * budget)
             panel_bytes = budget;
     }

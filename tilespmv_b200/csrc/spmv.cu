@@ -858,7 +858,10 @@ static int set_kernel_attrs(int stages, int warps, int smem_optin)
     TSP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
     // prefer L1: the driver still has to provide the dynamic shared memory a launch asks for, so streaming plans
     // (221 KB) get the 228 KB carve-out as before, while gather-bound plans (<= gather_smem_cap) leave >= 92 KB of L1
-    TSP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+    int carve = 0;
+    if (const char *e = getenv("TILESPMV_CARVEOUT")) // experiments only
+        carve = atoi(e);
+    TSP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     return TILESPMV_OK;
 }
 
