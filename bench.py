@@ -186,7 +186,7 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = "WARN"  # the box may export NCCL_DEBUG=VERSION, which prints a banner on stdout
+        os.environ.pop("NCCL_DEBUG", None)  # the box exports NCCL_DEBUG=VERSION/WARN, which prints a banner on stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L = _capi.load()
     G = args.grid
