@@ -587,13 +587,20 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long 
             __syncthreads();
             if (threadIdx.x == 0)
             {
+                // rows with >= SIDE_LONG_ROW entries (pieces of hub rows) are summed by the whole warp, the others by
+                // 4 lanes per row pair in nit trips
                 int nit = 0;
+                unsigned longmask = 0;
                 for (int r = 0; r < TS; r++)
                 {
                     const int len = s_start[r + 1] - s_start[r];
-                    nit = max(nit, (len + 3) >> 2);
+                    if (len >= SIDE_LONG_ROW)
+                        longmask |= 1u << r;
+                    else
+                        nit = max(nit, (len + 3) >> 2);
                 }
                 reinterpret_cast<RowRec *>(out + CHUNK_OFF_ROWS + 16 * k)->side_nit = (uint16_t)nit;
+                reinterpret_cast<uint16_t *>(out + hdr.off_sidehdr + SIDEHDR_BYTES * (uint32_t)sb[4])[TS + 1] = (uint16_t)longmask;
             }
             __syncthreads();
         }

@@ -613,6 +613,16 @@ __device__ __forceinline__ void process_chunk(const unsigned char *st, uint32_t 
             const uint32_t s1 = w0 >> 16, e1 = w1 & 0xffffu;
             uint32_t k0 = (w0 & 0xffffu) + (uint32_t)g, k1 = s1 + (uint32_t)g;
             const int nit = (int)(rec.z >> 16);
+            // rows with many entries (pieces of hub rows of power-law matrices) would keep 4 lanes busy for hundreds
+            // of trips: the whole warp sums them instead (below), this loop skips them
+            const uint32_t longmask = wt >> 16;
+            if (longmask)
+            {
+                if ((longmask >> (2 * p)) & 1u)
+                    k0 = s1;
+                if ((longmask >> (2 * p + 1)) & 1u)
+                    k1 = e1;
+            }
 #pragma unroll 1
             for (int i = 0; i < nit; i += 2) // trips past a lane's last entry are predicated off
             {
@@ -626,6 +636,45 @@ __device__ __forceinline__ void process_chunk(const unsigned char *st, uint32_t 
                     a1 = fma_t<T>(sideval[k1 + 4u], xside[k1 + 4u], a1);
                 k0 += 8u;
                 k1 += 8u;
+            }
+            if (longmask) // warp-uniform
+            {
+                const uint32_t hdr0_s = sidehdr_s - 4u * (uint32_t)p;
+                uint32_t lm = longmask;
+#pragma unroll 1
+                while (lm)
+                {
+                    const int r = __ffs((int)lm) - 1;
+                    lm &= lm - 1u;
+                    const uint32_t se = lds_u32(hdr0_s + 2u * (uint32_t)(r & ~1));         // starts of rows r&~1, (r&~1)+1
+                    const uint32_t nx = lds_u16(hdr0_s + 2u * (uint32_t)(r & ~1) + 4u);    // start of row (r&~1)+2
+                    const uint32_t s = (r & 1) ? se >> 16 : se & 0xffffu, e = (r & 1) ? nx : se >> 16;
+                    T c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll 1
+                    for (uint32_t q = s + (uint32_t)lane; q < e; q += 128u)
+                    {
+                        c0 = fma_t<T>(sideval[q], xside[q], c0);
+                        if (q + 32u < e)
+                            c1 = fma_t<T>(sideval[q + 32u], xside[q + 32u], c1);
+                        if (q + 64u < e)
+                            c2 = fma_t<T>(sideval[q + 64u], xside[q + 64u], c2);
+                        if (q + 96u < e)
+                            c3 = fma_t<T>(sideval[q + 96u], xside[q + 96u], c3);
+                    }
+                    T c = (c0 + c1) + (c2 + c3);
+                    c += __shfl_xor_sync(0xffffffffu, c, 16);
+                    c += __shfl_xor_sync(0xffffffffu, c, 8);
+                    c += __shfl_xor_sync(0xffffffffu, c, 4);
+                    c += __shfl_xor_sync(0xffffffffu, c, 2);
+                    c += __shfl_xor_sync(0xffffffffu, c, 1);
+                    if (lane == (r >> 1)) // lane (g = 0, p = r / 2) carries the sum into the row's accumulator
+                    {
+                        if (r & 1)
+                            a1 += c;
+                        else
+                            a0 += c;
+                    }
+                }
             }
             const uint32_t total = wt & 0xffffu;
             sideval += total;

@@ -8,7 +8,7 @@
 //   ChunkHeader                          32 B
 //   RowRec   [nrows]                     16 B each  block rows (or pieces of long block rows)
 //   ODesc    [nother]                     8 B each  descriptors of the non-ELL tiles, pad 16
-//   SideHdr  [#rows with side][20] u16   40 B each  17 exclusive row starts of the extracted nnz, pad 16
+//   SideHdr  [#rows with side][20] u16   40 B each  17 exclusive row starts of the extracted nnz + mask of long rows, pad 16
 //   SideVal  [nside] T                   pad 16
 //   payload, row after row:
 //     ELL group of the row -- ALL slot-rows (16 values, one per local row) of its ELL/HYB tiles,
@@ -75,7 +75,8 @@ struct RowRec // 16 B, one 128-bit shared-memory load
 static_assert(sizeof(RowRec) == 16, "RowRec must be 16 bytes");
 constexpr uint32_t ROW_PARTIAL = 0x80000000u;
 constexpr uint32_t ROWF_HAS_SIDE = 1u;
-constexpr uint32_t SIDEHDR_BYTES = 40; // 17 x u16 used
+constexpr uint32_t SIDEHDR_BYTES = 40; // 17 x u16 row starts + u16 mask of the long rows
+constexpr int SIDE_LONG_ROW = 32;      // local rows with at least this many side entries are summed by the whole warp
 
 // ODesc as uint2: x = format | xsel << 8 | width << 16 ; y = aux (CSR nnz, DenseRow row mask)
 constexpr int TSP_FMT_CSRGROUP = 8;      // ODesc: xsel = first x segment of the row, width = slot-rows, aux = entries
