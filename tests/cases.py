@@ -101,7 +101,22 @@ HYB_CASES = {
     "banded_2k_real": lambda: g.banded(2048, val_mode=0),
 }
 
+def _hub_rows(m=256, n=8192, seed=21):
+    """A few very long rows among very sparse ones: row 3 has 5000 entries (cut into pieces, every piece one
+    long local row), row 100 has 40 (long, inside a whole block row), row 101 has 31 (just short), the rest 1-2."""
+    rng = np.random.default_rng(seed)
+    rp = np.zeros(m + 1, np.int32)
+    cols = []
+    for i in range(m):
+        k = {3: 5000, 100: 40, 101: 31, 200: 700}.get(i, int(rng.integers(1, 3)))
+        cols.extend(sorted(rng.choice(n, size=k, replace=False).tolist()))
+        rp[i + 1] = len(cols)
+    ci = np.array(cols, np.int32)
+    return m, n, rp, ci, rng.uniform(-1, 1, len(ci))
+
+
 CASES = {
+    "hub_rows": _hub_rows,
     "seven_formats": lambda: g.seven_formats(),
     "lap2d_64": lambda: g.lap2d(64, val_mode=1),
     "lap3d27_24": lambda: g.lap3d27(24, val_mode=1),

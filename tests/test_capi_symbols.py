@@ -98,3 +98,68 @@ def test_mmio_front_end_matches_oracle(tmp_path):
     bad = str(tmp_path / "bad.mtx")
     open(bad, "w").write("hello world\n1 1 1\n")
     assert api.mmio_allinone(bad)[0] == -2
+
+
+def _same(got, want):
+    assert got[:3] == want[:3]
+    for a, b in zip(got[3:], want[3:]):
+        assert a.tobytes() == b.tobytes()
+
+
+def test_mmio_parallel_parser_cache_and_fallback(tmp_path, monkeypatch):
+    """Files with >= 4096 entries take the parallel parser; anything unusual falls back to the serial loop that
+    mimics the reference's fscanf.  Every variant must equal the oracle's reader (itself pinned against the reference's
+    mmio_allinone).  TILESPMV_MTX_CACHE switches on the binary CSR cache."""
+    from oracle import oracle_py as O
+    from tilespmv_b200 import generators as g
+    ora = O.Oracle("f64")
+    m, n, rp, ci, v = g.rmat(11, val_mode=0)  # ~25 k entries, rows of very different lengths
+    big = str(tmp_path / "big.mtx")
+    g.write_mtx(big, m, n, rp, ci, v)
+    rc, got = api.mmio_allinone(big)
+    rco, want = ora.mtx_read(big)
+    assert rc == rco == 0
+    _same(got, want)
+    # symmetric pattern file, exponent / signed values, tabs, blank lines at the end
+    rng = np.random.default_rng(3)
+    sym = str(tmp_path / "sym.mtx")
+    with open(sym, "w") as f:
+        pairs = sorted({(int(max(a, b)), int(min(a, b))) for a, b in rng.integers(1, 3000, size=(6000, 2))})
+        f.write("%%MatrixMarket matrix coordinate pattern symmetric\n% a comment\n%another\n")
+        f.write(f"3000 3000 {len(pairs)}\n")
+        for a, b in pairs:
+            f.write(f"{a}\t{b}\n")
+        f.write("\n\n")
+    val = str(tmp_path / "val.mtx")
+    with open(val, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n2000 1000 5000\n")
+        for k in range(5000):
+            x = [f"{rng.uniform(-1, 1):.17e}", f"+{rng.uniform(0, 9):.3f}", f"{rng.integers(-5, 5)}", "1e-3", "-.5"][k % 5]
+            f.write(f"  {rng.integers(1, 2001)} {rng.integers(1, 1001)}   {x}  \n")
+    for p in (sym, val):
+        rc, got = api.mmio_allinone(p)
+        rco, want = ora.mtx_read(p)
+        assert rc == rco == 0
+        _same(got, want)
+    # an out-of-range index in the middle (undefined behaviour upstream: it would write out of bounds): the parallel
+    # parser hands over to the serial loop, which stops at the first invalid entry
+    bad = str(tmp_path / "bad.mtx")
+    lines = open(val).read().split("\n")
+    lines[2500] = "99999 1 1.0"
+    open(bad, "w").write("\n".join(lines))
+    rc, got = api.mmio_allinone(bad)
+    assert rc == 0 and len(got[4]) == 2498
+    rcv, full = api.mmio_allinone(val)
+    order = np.argsort(np.repeat(np.arange(2000), np.diff(full[3])), kind="stable")  # rows are in file order
+    assert len(full[4]) == 5000 and order is not None
+    # binary cache: second read comes from the cache file and is identical; a changed source invalidates it
+    cache = tmp_path / "cache"
+    cache.mkdir()
+    monkeypatch.setenv("TILESPMV_MTX_CACHE", str(cache))
+    rc, first = api.mmio_allinone(big)
+    assert rc == 0 and len(list(cache.iterdir())) == 1
+    rc, second = api.mmio_allinone(big)
+    _same(second, first)
+    _same(second, ora.mtx_read(big)[1])
+    rc, f32 = api.mmio_allinone(big, api.F32)
+    assert rc == 0 and f32[5].dtype == np.float32 and len(list(cache.iterdir())) == 2

@@ -73,7 +73,7 @@ def test_convert_and_spmv_f64(name):
 
 
 @pytest.mark.parametrize("name", ["seven_formats", "lap2d_64", "banded_8k_real", "rmat_12_real", "ragged_band",
-                                  "band_unsorted", "ragged_seven", "uniform_8k", "dense_48"])
+                                  "band_unsorted", "ragged_seven", "uniform_8k", "dense_48", "hub_rows"])
 def test_convert_and_spmv_f32(name):
     check_matrix(CASES[name](), "f32")
 
@@ -94,7 +94,7 @@ def test_csr_groups_and_individual_csr_tiles_agree(name, precision):
 @pytest.mark.parametrize("name,precision,panel", [("uniform_8k", "f64", 8192), ("uniform_8k", "f32", 4096), ("rmat_12", "f64", 4096),
                                                   ("rmat_12_real", "f32", 1024), ("ragged_rmat", "f64", 2048),
                                                   ("seven_formats", "f64", 128), ("lap2d_64", "f64", 4096),
-                                                  ("empty_rows", "f64", 128), ("band_contig_8k", "f64", 8192)])
+                                                  ("empty_rows", "f64", 128), ("band_contig_8k", "f64", 8192), ("hub_rows", "f64", 8192)])
 def test_x_panels_accumulating_sub_plans(name, precision, panel):
     """xpanel_bytes forces the side matrix into column panels (one accumulating launch per panel, the layout
     meant for x far larger than L2): same results, also with rows cut into pieces inside a panel."""

@@ -1,9 +1,12 @@
 // capi.cu -- the extern "C" surface of include/tilespmv.h: error state, dmat upload / export,
 // the drop-in entry points (Tile_create, Tile_destroy, tilespmv_prepare, call_tilespmv_cuda),
 // the plan API and the Matrix Market front end.
+#include <omp.h>
+#include <sys/stat.h>
 #include <sys/time.h>
 
 #include <cctype>
+#include <charconv>
 #include <new>
 
 #include "plan.cuh"
@@ -533,6 +536,65 @@ static void call_entry(char *filename, TM *matrix, int rowA, int colA, int nnzA,
 // ---------------------------------------------------------------------------------------------
 // Matrix Market front end (semantics of mmio_allinone, mmio_highlevel.h:593-759)
 // ---------------------------------------------------------------------------------------------
+// binary CSR cache of the Matrix Market front end: 8-byte magic, {sizeof(T), m, n, nnz, symmetric} as int32, then the
+// three arrays raw.  A file that does not match in every header field is ignored.
+static const char MTX_CACHE_MAGIC[8] = {'T', 'S', 'P', 'C', 'S', 'R', '1', 0};
+template <class T>
+static bool mtx_cache_load(const char *path, int *m, int *n, int *nnz, int *sym, int **rp, int **cj, T **cv)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f)
+        return false;
+    char magic[8];
+    int h[5];
+    bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, MTX_CACHE_MAGIC, 8) == 0 && fread(h, sizeof(int), 5, f) == 5 &&
+              h[0] == (int)sizeof(T) && h[1] >= 0 && h[2] >= 0 && h[3] >= 0;
+    int *a = nullptr, *b = nullptr;
+    T *c = nullptr;
+    if (ok)
+    {
+        const size_t nz = (size_t)h[3];
+        a = static_cast<int *>(malloc(((size_t)h[1] + 1) * sizeof(int)));
+        b = static_cast<int *>(malloc((nz ? nz : 1) * sizeof(int)));
+        c = static_cast<T *>(malloc((nz ? nz : 1) * sizeof(T)));
+        ok = a && b && c && fread(a, sizeof(int), (size_t)h[1] + 1, f) == (size_t)h[1] + 1 && fread(b, sizeof(int), nz, f) == nz &&
+             fread(c, sizeof(T), nz, f) == nz && a[h[1]] == h[3];
+    }
+    fclose(f);
+    if (!ok)
+    {
+        free(a);
+        free(b);
+        free(c);
+        return false;
+    }
+    *m = h[1];
+    *n = h[2];
+    *nnz = h[3];
+    *sym = h[4];
+    *rp = a;
+    *cj = b;
+    *cv = c;
+    return true;
+}
+template <class T>
+static void mtx_cache_store(const char *path, int m, int n, int nnz, int sym, const int *rp, const int *cj, const T *cv)
+{
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f)
+        return; // the cache is best effort
+    const int h[5] = {(int)sizeof(T), m, n, nnz, sym};
+    bool ok = fwrite(MTX_CACHE_MAGIC, 1, 8, f) == 8 && fwrite(h, sizeof(int), 5, f) == 5 &&
+              fwrite(rp, sizeof(int), (size_t)m + 1, f) == (size_t)m + 1 && fwrite(cj, sizeof(int), (size_t)nnz, f) == (size_t)nnz &&
+              fwrite(cv, sizeof(T), (size_t)nnz, f) == (size_t)nnz;
+    ok = fclose(f) == 0 && ok;
+    if (ok)
+        rename(tmp.c_str(), path);
+    else
+        remove(tmp.c_str());
+}
+
 template <class T>
 static int mmio_entry(int *m, int *n, int *nnz, int *isSymmetric, int **csrRowPtr, int **csrColIdx, T **csrVal,
                       const char *filename)
@@ -597,11 +659,135 @@ static int mmio_entry(int *m, int *n, int *nnz, int *isSymmetric, int **csrRowPt
     }
     if (M_ < 0 || N_ < 0 || NZ < 0 || M_ > 0x7ffffff0l || N_ > 0x7ffffff0l || NZ > 0x7ffffff0l)
         return -4;
+    // ---- binary cache of the parsed CSR (opt-in: TILESPMV_MTX_CACHE=<directory>), keyed by file name, size, mtime
+    std::string cache_path;
+    if (const char *dir = getenv("TILESPMV_MTX_CACHE"))
+    {
+        struct stat st;
+        if (dir[0] && stat(filename, &st) == 0)
+        {
+            const char *base = strrchr(filename, '/');
+            base = base ? base + 1 : filename;
+            char key[96];
+            snprintf(key, sizeof(key), ".%lld.%lld.f%d.tspcsr", (long long)st.st_size, (long long)st.st_mtime, (int)sizeof(T) * 8);
+            cache_path = std::string(dir) + "/" + base + key;
+            if (mtx_cache_load<T>(cache_path.c_str(), m, n, nnz, isSymmetric, csrRowPtr, csrColIdx, csrVal))
+                return 0;
+        }
+    }
     std::vector<int> ri((size_t)NZ), ci((size_t)NZ);
     std::vector<T> vv((size_t)NZ);
     std::vector<int> cnt((size_t)M_ + 1, 0);
     long e = 0;
-    for (; e < NZ; e++)
+    // ---- parallel parse: the body is cut at line ends into one piece per thread; pass 1 counts the entry lines of
+    //      every piece, pass 2 parses them straight into place.  Anything unusual (a malformed or out-of-range
+    //      entry, fewer lines than the size line promises) falls back to the serial loop below, which reproduces
+    //      the reference's fscanf behaviour token by token.
+    bool parsed = false;
+    if (NZ >= 4096)
+    {
+        const int nt = std::max(1, std::min(omp_get_max_threads(), 64));
+        std::vector<const char *> cut((size_t)nt + 1);
+        cut[0] = p;
+        cut[nt] = end;
+        for (int t = 1; t < nt; t++)
+        {
+            const char *q = p + (size_t)(end - p) * (size_t)t / (size_t)nt;
+            cut[t] = std::max(cut[t - 1], next_line(q));
+        }
+        std::vector<long> lines((size_t)nt + 1, 0);
+        int bad = 0;
+#pragma omp parallel num_threads(nt)
+        {
+            const int t = omp_get_thread_num();
+            long c = 0;
+            for (const char *q = cut[t]; q < cut[t + 1];)
+            {
+                const char *l = q;
+                q = next_line(q);
+                while (l < q && isspace((unsigned char)*l))
+                    l++;
+                c += l < q ? 1 : 0;
+            }
+            lines[(size_t)t + 1] = c;
+#pragma omp barrier
+#pragma omp single
+            for (int k = 0; k < nt; k++)
+                lines[(size_t)k + 1] += lines[(size_t)k];
+            long idx = lines[(size_t)t];
+            int mybad = 0;
+            for (const char *q = cut[t]; q < cut[t + 1] && idx < NZ && !mybad;)
+            {
+                const char *l = q;
+                q = next_line(q);
+                const char *le = q; // one past the line (incl. its newline)
+                while (l < le && isspace((unsigned char)*l))
+                    l++;
+                if (l >= le)
+                    continue;
+                long a = 0, b = 0;
+                double re = 1.0;
+                auto rint = [&](long &out) {
+                    while (l < le && (*l == ' ' || *l == '\t'))
+                        l++;
+                    if (l < le && *l == '+')
+                        l++;
+                    auto r = std::from_chars(l, le, out);
+                    if (r.ec != std::errc())
+                        return false;
+                    l = r.ptr;
+                    return true;
+                };
+                auto rdbl = [&](double &out) {
+                    while (l < le && (*l == ' ' || *l == '\t'))
+                        l++;
+                    if (l < le && *l == '+')
+                        l++;
+                    auto r = std::from_chars(l, le, out);
+                    if (r.ec != std::errc())
+                        return false;
+                    l = r.ptr;
+                    return true;
+                };
+                bool ok = rint(a) && rint(b);
+                if (ok && !is_pattern)
+                {
+                    ok = rdbl(re);
+                    double im;
+                    if (ok && is_complex)
+                        ok = rdbl(im);
+                }
+                while (ok && l < le && isspace((unsigned char)*l))
+                    l++;
+                if (!ok || l < le || a < 1 || a > M_ || b < 1 || b > N_)
+                {
+                    mybad = 1;
+                    break;
+                }
+                ri[(size_t)idx] = (int)a - 1;
+                ci[(size_t)idx] = (int)b - 1;
+                vv[(size_t)idx] = (T)re;
+                idx++;
+            }
+            if (mybad)
+            {
+#pragma omp atomic write
+                bad = 1;
+            }
+        }
+        if (!bad && lines[(size_t)nt] >= NZ)
+        {
+            parsed = true;
+            e = NZ;
+            for (long k = 0; k < NZ; k++)
+            {
+                cnt[ri[(size_t)k]]++;
+                if (symm && ri[(size_t)k] != ci[(size_t)k])
+                    cnt[ci[(size_t)k]]++;
+            }
+        }
+    }
+    for (; !parsed && e < NZ; e++)
     {
         char *q;
         long a = strtol(p, &q, 10);
@@ -674,6 +860,8 @@ static int mmio_entry(int *m, int *n, int *nnz, int *isSymmetric, int **csrRowPt
     *csrRowPtr = rp;
     *csrColIdx = cj;
     *csrVal = cv;
+    if (!cache_path.empty())
+        mtx_cache_store<T>(cache_path.c_str(), *m, *n, *nnz, *isSymmetric, rp, cj, cv);
     return 0;
 }
 
