@@ -150,6 +150,35 @@ BIG_CASES = {
 }
 
 
+def random_case(rng):
+    """A random CSR matrix mixing the structures that select different tile formats: dense blocks, full rows / columns
+    inside a tile, bands, scattered entries, hub rows, empty rows; dimensions are not multiples of 16."""
+    m, n = int(rng.integers(1, 400)), int(rng.integers(1, 400))
+    A = np.zeros((m, n), bool)
+    for _ in range(int(rng.integers(0, 6))):  # dense-ish blocks
+        r0, c0 = int(rng.integers(0, m)), int(rng.integers(0, n))
+        h, w = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        A[r0:r0 + h, c0:c0 + w] |= rng.random((min(h, m - r0), min(w, n - c0))) < rng.choice([0.3, 0.8, 1.0])
+    for _ in range(int(rng.integers(0, 4))):  # full rows / columns (DenseRow / DenseCol tiles)
+        if rng.random() < 0.5:
+            A[int(rng.integers(0, m)), :] = True
+        else:
+            A[:, int(rng.integers(0, n))] = True
+    if rng.random() < 0.5:  # band
+        hb = int(rng.integers(1, 24))
+        i, j = np.indices((m, n))
+        A |= (np.abs(i - j) <= hb) & (rng.random((m, n)) < rng.choice([0.4, 1.0]))
+    A |= rng.random((m, n)) < rng.choice([0.0, 0.002, 0.02, 0.1])  # scattered
+    if rng.random() < 0.3:
+        A[int(rng.integers(0, m)):, :] = False  # empty tail
+    rows, cols = np.nonzero(A)
+    rp = np.zeros(m + 1, np.int32)
+    np.add.at(rp, rows + 1, 1)
+    rp = np.cumsum(rp).astype(np.int32)
+    v = rng.uniform(-1, 1, len(cols))
+    return m, n, rp, cols.astype(np.int32), v
+
+
 def x_for(n, mode, dtype=np.float64, seed=7):
     """mode 1: x[i] = i % 10 like main.cu:93-97; mode 0: seeded uniform(-1,1)."""
     if mode == 1:

@@ -14,7 +14,7 @@ import pytest
 
 from oracle import oracle_py as O
 from tests import golden_util as G
-from tests.cases import BIG_CASES, CASES, x_for
+from tests.cases import BIG_CASES, CASES, random_case, x_for
 from tilespmv_b200 import api
 
 pytestmark = pytest.mark.gpu
@@ -268,3 +268,50 @@ def test_reduced_configs_3_4_5_and_size_independent_properties(name, precision):
     sel = ci == j
     np.add.at(want, rows[sel], v[sel].astype(np.float64))
     assert np.array_equal(col.astype(np.float64), want.astype(dt).astype(np.float64))
+
+
+def _y_against_csr(case, precision, plan_kwargs=None):
+    """y through the library vs the plain CSR loop (main.cu:101-110) for inputs whose conversion the oracle would
+    take too long to restate; tolerance relative to sum |a||x| as everywhere."""
+    m, n, rp, ci, v = case
+    dt = np.float64 if precision == "f64" else np.float32
+    v = v.astype(dt)
+    dm = api.DeviceTileMatrix.from_csr(m, n, rp, ci, v)
+    plan = api.Plan(dm, **(plan_kwargs or {}))
+    x = np.random.default_rng(11).uniform(-1, 1, n).astype(dt)
+    y = plan.spmv_host(x)
+    ora = O.Oracle(precision)
+    y_ref = ora.csr_spmv(m, rp, ci, v, x, parallel=True)
+    scale = ora.csr_abs_spmv(m, rp, ci, v, x)
+    assert_y_close(y, y_ref, scale, precision)
+    return dm.info(), plan.info()
+
+
+def test_config5_shard_at_full_width_uses_x_panels():
+    """One row block of BASELINE config 5 at its true width: 1 M rows x 50 M columns, 20 per row.  x is 400 MB, far
+    larger than L2, so the planner cuts the side matrix into column panels on its own."""
+    from tilespmv_b200 import generators as g
+    di, pi = _y_against_csr(g.uniform_rows(50_000_000, 0, 1 << 20, val_mode=0), "f64")
+    assert di.nnz_side == di.nnz == 20 << 20
+    assert pi.xpanels > 1 and pi.launches_per_spmv >= pi.xpanels
+
+
+def test_config4_rmat_scale_22_fp32_hub_rows():
+    """BASELINE config 4 at scale 22 (65 M nnz, fp32): almost everything is extracted side entries, hub rows are cut
+    into hundreds of pieces whose partial sums the fix-up kernels add."""
+    from tilespmv_b200 import generators as g
+    di, pi = _y_against_csr(g.rmat(22, val_mode=0), "f32")
+    assert di.nnz_side > 0.9 * di.nnz and pi.split_rows > 0 and pi.launches_per_spmv >= 2
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_matrices_all_plan_variants(seed):
+    """Differential test: conversion bit-exact against the oracle, y against tilespmv_cpu, for every plan variant
+    (CSR groups on / off, x panels, tiny chunks that cut rows, HYB rule) on random structure."""
+    rng = np.random.default_rng(1000 + seed)
+    case = random_case(rng)
+    precision = "f64" if seed % 3 else "f32"
+    variants = [dict(), dict(csr_groups=False), dict(xpanel_bytes=256), dict(chunk_bytes=2560, xstage_bytes=128),
+                dict(chunk_bytes=2560, xstage_bytes=256, xpanel_bytes=512, csr_groups=False)]
+    check_matrix(case, precision, plan_kwargs=variants[seed % len(variants)], enable_hyb=seed % 4 == 0)
+    check_matrix(case, precision, plan_kwargs=variants[(seed + 1) % len(variants)])

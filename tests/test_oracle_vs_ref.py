@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle_py as O
-from tests.cases import BIG_CASES, CASES, x_for
+from tests.cases import BIG_CASES, CASES, random_case, x_for
 
 pytestmark = pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref not built")
 
@@ -57,6 +57,12 @@ def test_oracle_matches_reference_f32(name):
 @pytest.mark.parametrize("name", sorted(BIG_CASES))
 def test_oracle_matches_reference_big(name):
     _compare(BIG_CASES[name](), "f64")
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_oracle_matches_reference_on_random_structure(seed):
+    """The inputs of the GPU differential test (tests/test_gpu_parity.py): all seven formats occur."""
+    _compare(random_case(np.random.default_rng(1000 + seed)), "f64" if seed % 3 else "f32")
 
 
 def test_seven_format_fixture_values():
