@@ -774,6 +774,10 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
         return groupable(b) ? row_ob2[b] + (long long)csr_group_bytes((uint32_t)row_cs[b], (uint32_t)row_cn[b], vs) : row_ob[b];
     };
     auto row_other_count = [&](int b) { return groupable(b) ? row_no2[b] + 1 : row_no[b]; };
+    // mostly extracted (side) entries among the nonzeros THIS (sub-)plan handles?  (also drives the shared-memory cap)
+    const int64_t my_side = (int64_t)row_s0[tilem] - row_s0[0], my_tiled = src.tiles ? dm->nnz - dm->coototal : 0;
+    const bool gather_bound = my_side > 0 && my_side >= my_tiled;
+    P->gather_bound = gather_bound;
     if (C == 0)
     {
         // Matrices made mostly of extracted entries: score of a candidate = resident warps per SM it leaves (2 stages +
@@ -795,10 +799,6 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
                     unfit[k] += bytes;
         }
         int pick = 0;
-        // mostly extracted (side) entries among the nonzeros THIS (sub-)plan handles?
-        const int64_t my_side = (int64_t)row_s0[tilem] - row_s0[0], my_tiled = src.tiles ? dm->nnz - dm->coototal : 0;
-        const bool gather_bound = my_side >= my_tiled;
-        P->gather_bound = gather_bound;
         if (total > 0 && gather_bound)
         {
             // scattered x gathers are latency-bound: resident warps matter more than rows cut into pieces
