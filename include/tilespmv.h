@@ -265,6 +265,15 @@ int tilespmv_plan_spmv_host(tilespmv_plan *plan, const void *x, void *y);
 int tilespmv_plan_spmv_host_batch(tilespmv_plan *plan, int nvec, const void *const *x, void *const *y);
 
 /*
+ * Repeated SpMV on ONE GPU, x <- A*x for a square matrix: iteration i reads d_xa (i even) or d_xb (i odd) and writes
+ * the other buffer, so the result is in d_xa when niters is even, else in d_xb.  The niters launches are captured once
+ * into a CUDA graph (re-instantiated only when the buffers or niters change) and replayed with a single graph launch on
+ * `stream`: no per-iteration CPU launch cost, which matters for matrices whose SpMV takes a few microseconds.
+ * Both buffers are DEVICE pointers with rowA = colA entries, 16-byte aligned.  Not available while peers are set.
+ */
+int tilespmv_plan_iterate(tilespmv_plan *plan, void *d_xa, void *d_xb, int niters, void *stream);
+
+/*
  * Multi-GPU repeated SpMV (row-block sharding, x replicated): after computing its rows the
  * kernel also stores them straight into x_next of every peer (P2P-mapped pointers over NVLink)
  * at row_offset, so the all-gather of the next x is the kernel's own store stream.

@@ -193,6 +193,35 @@ def test_host_batch_pipeline_equals_single_calls():
     plan.spmv_host_batch([], [])
 
 
+@pytest.mark.parametrize("name", ["lap2d_64", "rmat_12_real", "band_contig_8k"])
+def test_iterate_graph_equals_a_loop_of_spmv_calls(name):
+    """tilespmv_plan_iterate (niters ping-pong launches replayed as one CUDA graph) is bit-identical to calling
+    tilespmv_plan_spmv in a loop; the graph is re-used across calls and rebuilt when niters changes."""
+    import torch
+    m, n, rp, ci, v = CASES[name]()
+    assert m == n
+    dm = api.DeviceTileMatrix.from_csr(m, n, rp, ci, v * 0.01)
+    plan = api.Plan(dm, chunk_bytes=2560, xstage_bytes=256) if name == "rmat_12_real" else api.Plan(dm)
+    x0 = torch.from_numpy(np.random.default_rng(2).uniform(-1, 1, n)).cuda()
+    launches0 = api._capi.load().tilespmv_kernel_launch_count()
+    for niters in (5, 5, 4, 1):
+        a, b = x0.clone(), torch.empty_like(x0)
+        for i in range(niters):
+            src, dst = (a, b) if i % 2 == 0 else (b, a)
+            plan.spmv(src.data_ptr(), dst.data_ptr())
+        want = (a if niters % 2 == 0 else b).clone()
+        xa, xb = x0.clone(), torch.full_like(x0, float("nan"))
+        plan.iterate(xa.data_ptr(), xb.data_ptr(), niters)
+        torch.cuda.synchronize()
+        got = xa if niters % 2 == 0 else xb
+        assert torch.equal(got, want), niters
+    per = plan.info().launches_per_spmv
+    assert api._capi.load().tilespmv_kernel_launch_count() - launches0 == 2 * (5 + 5 + 4 + 1) * per
+    with pytest.raises(api.TileSpMVError):
+        m2, n2, rp2, ci2, v2 = CASES["seven_formats"]()  # 32 x 40: not square
+        api.Plan(api.DeviceTileMatrix.from_csr(m2, n2, rp2, ci2, v2)).iterate(xa.data_ptr(), xb.data_ptr(), 2)
+
+
 def test_device_pointer_path_streams_and_linearity():
     """tilespmv_plan_spmv on torch device buffers and a non-default stream; A(ax+by) = aAx + bAy."""
     import torch

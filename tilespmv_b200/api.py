@@ -213,6 +213,12 @@ class Plan:
         ya = (C.c_void_p * max(n, 1))(*[C.c_void_p(p) for p in y_ptrs])
         check(_capi.load().tilespmv_plan_spmv_host_batch(self.handle, n, xa, ya), "tilespmv_plan_spmv_host_batch")
 
+    def iterate(self, d_xa, d_xb, niters, stream=0):
+        """x <- A*x niters times, ping-pong between two device buffers, replayed as one CUDA graph; the result is in
+        d_xa when niters is even, else in d_xb (tilespmv_plan_iterate)."""
+        check(_capi.load().tilespmv_plan_iterate(self.handle, C.c_void_p(d_xa), C.c_void_p(d_xb), niters,
+                                                  C.c_void_p(stream)), "tilespmv_plan_iterate")
+
     def time(self, d_x, d_y, warmup=3, iters=20, stream=0):
         ms = C.c_double(0)
         check(_capi.load().tilespmv_plan_time(self.handle, C.c_void_p(d_x), C.c_void_p(d_y), warmup, iters,

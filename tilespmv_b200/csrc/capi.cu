@@ -1071,6 +1071,69 @@ int tilespmv_plan_spmv_host_batch(tilespmv_plan *plan, int nvec, const void *con
     return TILESPMV_OK;
 }
 
+int tilespmv_plan_iterate(tilespmv_plan *plan, void *d_xa, void *d_xb, int niters, void *stream)
+{
+    if (!plan || niters < 0 || ((!d_xa || !d_xb) && plan->rowA))
+    {
+        set_error("plan_iterate: invalid argument");
+        return TILESPMV_ERR_INVALID;
+    }
+    if (plan->rowA != plan->colA)
+    {
+        set_error("plan_iterate: x <- A*x needs a square matrix (%d x %d)", plan->rowA, plan->colA);
+        return TILESPMV_ERR_INVALID;
+    }
+    if (plan->npeers > 0)
+    {
+        set_error("plan_iterate: with peers set every iteration needs a cross-GPU barrier; drive the loop with tilespmv_plan_spmv");
+        return TILESPMV_ERR_UNSUPPORTED;
+    }
+    if (niters == 0 || plan->rowA == 0)
+        return TILESPMV_OK;
+    if (!plan->iter_exec || plan->iter_xa != d_xa || plan->iter_xb != d_xb || plan->iter_n != niters)
+    {
+        if (plan->iter_exec)
+        {
+            cudaGraphExecDestroy(plan->iter_exec);
+            plan->iter_exec = nullptr;
+        }
+        if (!plan->s_capture)
+            TSP_CUDA(cudaStreamCreateWithFlags(&plan->s_capture, cudaStreamNonBlocking));
+        const int64_t counted = g_launches.load(); // launches recorded while capturing are not executions
+        TSP_CUDA(cudaStreamBeginCapture(plan->s_capture, cudaStreamCaptureModeThreadLocal));
+        int rc = TILESPMV_OK;
+        for (int i = 0; i < niters && rc == TILESPMV_OK; i++)
+            rc = plan_launch(plan, (i & 1) ? d_xb : d_xa, (i & 1) ? d_xa : d_xb, plan->s_capture);
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(plan->s_capture, &graph);
+        g_launches.store(counted);
+        if (rc != TILESPMV_OK || e != cudaSuccess || !graph)
+        {
+            if (graph)
+                cudaGraphDestroy(graph);
+            if (rc == TILESPMV_OK)
+                set_error("plan_iterate: stream capture failed: %s", cudaGetErrorString(e));
+            return rc != TILESPMV_OK ? rc : TILESPMV_ERR_CUDA;
+        }
+        e = cudaGraphInstantiate(&plan->iter_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess)
+        {
+            plan->iter_exec = nullptr;
+            set_error("plan_iterate: cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+            return TILESPMV_ERR_CUDA;
+        }
+        plan->iter_xa = d_xa;
+        plan->iter_xb = d_xb;
+        plan->iter_n = niters;
+    }
+    TSP_CUDA(cudaGraphLaunch(plan->iter_exec, static_cast<cudaStream_t>(stream)));
+    tilespmv_plan_info info;
+    tilespmv_plan_get_info(plan, &info);
+    g_launches.fetch_add((int64_t)niters * info.launches_per_spmv, std::memory_order_relaxed);
+    return TILESPMV_OK;
+}
+
 int tilespmv_plan_set_peers(tilespmv_plan *plan, int npeers, void *const *peer_x, int64_t row_offset)
 {
     if (!plan || npeers < 0 || npeers > TSP_MAX_PEERS || (npeers > 0 && !peer_x))

@@ -65,8 +65,18 @@ struct tilespmv_plan
     tsp::DevBuf bx[HOST_RING], by[HOST_RING];
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[HOST_RING] = {nullptr}, ev_comp[HOST_RING] = {nullptr}, ev_out[HOST_RING] = {nullptr};
+    // tilespmv_plan_iterate: the niters ping-pong launches captured once into a CUDA graph, re-instantiated only
+    // when the buffers or the count change
+    cudaStream_t s_capture = nullptr;
+    cudaGraphExec_t iter_exec = nullptr;
+    void *iter_xa = nullptr, *iter_xb = nullptr;
+    int iter_n = 0;
     ~tilespmv_plan()
     {
+        if (iter_exec)
+            cudaGraphExecDestroy(iter_exec);
+        if (s_capture)
+            cudaStreamDestroy(s_capture);
         for (tilespmv_plan *q : sub)
             delete q;
         for (int i = 0; i < HOST_RING; i++)
