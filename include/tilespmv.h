@@ -227,6 +227,8 @@ typedef struct
     int64_t nnz_side;     /* coototal: nonzeros served from the extracted side CSR */
     int64_t tiles_by_format[7];
     int64_t device_bytes; /* bytes of device memory held by the dmat */
+    int64_t slots_by_format[7]; /* stored value slots per format (csrsize, coosize, ellsize, hybsize, dnssize,
+                                   dnsrowsize, dnscolsize of format.h): slots - nonzeros = padding of the format */
 } tilespmv_dmat_info;
 int tilespmv_dmat_get_info(const tilespmv_dmat *dm, tilespmv_dmat_info *info);
 

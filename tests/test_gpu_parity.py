@@ -48,6 +48,8 @@ def check_matrix(case, precision, plan_kwargs=None, exact_modes=(1,), real_modes
     info = dm.info()
     assert info.tilenum == Mo.tilenum and info.nnz == int(rp[m]) and info.nnz_side == Mo.coototal
     assert list(info.tiles_by_format) == [int((want["Format"] == f).sum()) for f in range(7)]
+    sc = want["scalars"]  # tilem, tilen, tilenum, csrsize, csrptrlen, coosize, ellsize, hybsize, hybellsize, hybcoosize, dns...
+    assert list(info.slots_by_format) == [int(sc[3]), int(sc[5]), int(sc[6]), int(sc[7]), int(sc[10]), int(sc[11]), int(sc[12])]
     # --- SpMV ---
     plan = api.Plan(dm, **(plan_kwargs or {}))
     integer_vals = bool(np.all(v == np.round(v)))

@@ -58,7 +58,7 @@ TileMatrixF32 = _tile_matrix(C.c_float, "Tile_matrix_f32")
 class DmatInfo(C.Structure):
     _fields_ = [("precision", C.c_int), ("rowA", C.c_int), ("colA", C.c_int), ("tilem", C.c_int),
                 ("tilen", C.c_int), ("tilenum", C.c_int), ("nnz", C.c_int64), ("nnz_side", C.c_int64),
-                ("tiles_by_format", C.c_int64 * 7), ("device_bytes", C.c_int64)]
+                ("tiles_by_format", C.c_int64 * 7), ("device_bytes", C.c_int64), ("slots_by_format", C.c_int64 * 7)]
 
 
 class PlanOptions(C.Structure):

@@ -959,6 +959,11 @@ int tilespmv_dmat_get_info(const tilespmv_dmat *dm, tilespmv_dmat_info *info)
     info->nnz_side = dm->coototal;
     for (int f = 0; f < 7; f++)
         info->tiles_by_format[f] = dm->fmt_hist[f];
+    // stored slots per format = the per-format sizes of the reference's size pass (csr2tile.h:754-793): with
+    // tiles_by_format and nnz this is the padding each format carries (cf. DEBUG_FORMATCOST, tilespmv_cuda.h:102-111)
+    const int slots[7] = {dm->csrsize, dm->coosize, dm->ellsize, dm->hybsize, dm->dnssize, dm->dnsrowsize, dm->dnscolsize};
+    for (int f = 0; f < 7; f++)
+        info->slots_by_format[f] = slots[f];
     info->device_bytes = dm->device_bytes();
     return TILESPMV_OK;
 }
