@@ -139,7 +139,11 @@ def cpu_baseline(steps=3):
             times.append(ms)
     nnz = int(rp[m])
     best = min(times)
+    t0 = time.time()
+    ora.csr_spmv(m, rp, ci, v, x)  # context only: the plain serial CSR loop of main.cu:101-110 on the same matrix
+    t_csr = time.time() - t0
     return {"value": 2.0 * nnz / (best * 1e-3) / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
+            "plain_csr_serial_gflops": 2.0 * nnz / t_csr / 1e9,
             "sample": f"3-D 27-pt Laplacian {G}^3 fp64 ({nnz} nnz: the whole config-2 matrix), "
                       f"tilespmv_cpu whole call, best of {steps}; Tile_matrix built by the oracle port in {t_conv:.1f}s "
                       f"with {ora.threads()} threads (untimed)",
@@ -253,6 +257,21 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t)
         nnz_total = int(t.item())
     value = 2.0 * nnz_total / (ms_step * 1e-3) / 1e9
+
+    # per-launch distribution (outside the timed region): 200 launches, one CUDA-event pair each (SURVEY 8d asks for the
+    # batch time AND the spread; the batch figure above is the reported one)
+    per_launch = None
+    if rank == 0:
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(200)]
+        for a_, b_ in evs:
+            a_.record()
+            plan.spmv(x.data_ptr(), y.data_ptr(), stream)
+            b_.record()
+        torch.cuda.synchronize()
+        us = np.sort(np.array([a_.elapsed_time(b_) * 1e3 for a_, b_ in evs]))
+        per_launch = {"n": 200, "min": float(us[0]), "median": float(us[100]), "p95": float(us[189]), "max": float(us[-1]),
+                      "unit": "us", "note": "event pair around every launch: includes ~2 us of launch gap"}
+    barrier()
 
     # ---- end-to-end with HOST buffers (pinned), host<->device copies inside the timed region ----
     # N = 1: the C-ABI host-pointer call (H2D of x, SpMV, D2H of y).  N > 1: the host x is distributed like the
@@ -410,7 +429,8 @@ def run_ours(args, rank, world, local_rank):
                       "grid": pi.grid, "block": pi.block, "smem_bytes": pi.smem_bytes, "chunk_bytes": pi.chunk_bytes,
                       "xstage_bytes": pi.xstage_bytes, "launches_per_spmv": pi.launches_per_spmv,
                       "csr_bytes": pi.csr_bytes, "gen_s": t_gen, "convert_s_incl_h2d": t_conv, "plan_s": t_plan,
-                      "result_check_vs_torch_csr": ok, "library": os.path.basename(_capi.lib_path())},
+                      "result_check_vs_torch_csr": ok, "library": os.path.basename(_capi.lib_path()),
+                      "per_launch_us": per_launch},
         }
         if iterate:
             out["iterate"] = iterate
