@@ -165,6 +165,7 @@ struct PackArgs
     long long nw;        // lookahead distance = warps of the persistent grid
     int stages;          // TMA pipeline depth the stream is laid out for
     int head_stride;
+    int side_long_row;   // local rows with at least this many side entries are summed by the whole warp
     int *error_flag;
     // Tile_matrix (device)
     int rowA, colA, tilem, tilen;
@@ -594,7 +595,7 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long 
                 for (int r = 0; r < TS; r++)
                 {
                     const int len = s_start[r + 1] - s_start[r];
-                    if (len >= SIDE_LONG_ROW)
+                    if (len >= a.side_long_row)
                         longmask |= 1u << r;
                     else
                         nit = max(nit, (len + 3) >> 2);
@@ -1108,6 +1109,9 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
         a.nw = P->nw;
         a.stages = P->stages;
         a.head_stride = P->head_stride;
+        a.side_long_row = SIDE_LONG_ROW;
+        if (const char *e = getenv("TILESPMV_SIDE_LONG_ROW")) // experiments
+            a.side_long_row = atoi(e);
         a.error_flag = d_err.as<int>();
         a.rowA = dm->rowA;
         a.colA = dm->colA;

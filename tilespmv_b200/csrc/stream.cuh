@@ -76,7 +76,7 @@ static_assert(sizeof(RowRec) == 16, "RowRec must be 16 bytes");
 constexpr uint32_t ROW_PARTIAL = 0x80000000u;
 constexpr uint32_t ROWF_HAS_SIDE = 1u;
 constexpr uint32_t SIDEHDR_BYTES = 40; // 17 x u16 row starts + u16 mask of the long rows
-constexpr int SIDE_LONG_ROW = 32;      // local rows with at least this many side entries are summed by the whole warp
+constexpr int SIDE_LONG_ROW = 64;      // local rows with at least this many side entries are summed by the whole warp (R-MAT 2^21: 32 -> 198.7 us, 64 -> 194.2, 128 -> 197.8)
 
 // ODesc as uint2: x = format | xsel << 8 | width << 16 ; y = aux (CSR nnz, DenseRow row mask)
 constexpr int TSP_FMT_CSRGROUP = 8;      // ODesc: xsel = first x segment of the row, width = slot-rows, aux = entries
