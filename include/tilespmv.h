@@ -276,6 +276,14 @@ int tilespmv_plan_spmv_host_batch(tilespmv_plan *plan, int nvec, const void *con
 int tilespmv_plan_iterate(tilespmv_plan *plan, void *d_xa, void *d_xb, int niters, void *stream);
 
 /*
+ * Row-block sharding for nparts GPUs (host-only, needs no device): contiguous ranges of block rows cut where the prefix
+ * of streamed bytes per block row (the weights of B_alg) crosses g / nparts of the total, always at multiples of 16 rows
+ * so that tiles never straddle GPUs.  row_cuts[nparts + 1] receives the first row of every part and rowA at the end;
+ * part g converts / plans rows [row_cuts[g], row_cuts[g+1]) with global column indices.  The reference is single-GPU.
+ */
+int tilespmv_partition_rows(int precision, int rowA, const int *rowptr, int nparts, int *row_cuts);
+
+/*
  * Multi-GPU repeated SpMV (row-block sharding, x replicated): after computing its rows the
  * kernel also stores them straight into x_next of every peer (P2P-mapped pointers over NVLink)
  * at row_offset, so the all-gather of the next x is the kernel's own store stream.

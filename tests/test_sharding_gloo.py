@@ -39,6 +39,18 @@ def test_partition_tiles_the_block_rows_and_balances_bytes():
     assert rows[0][0] == 0 and rows[-1][1] == m and all(r0 % 16 == 0 for r0, _ in rows)
 
 
+def test_native_partition_equals_the_python_one():
+    """tilespmv_partition_rows (C-ABI, host-only) returns the cuts of sharding.partition + row_ranges."""
+    cases = [g.rmat(12, val_mode=1), g.banded(4096 + 16 * 3, val_mode=0), g.lap3d27(24, val_mode=1), g.uniform(2048, val_mode=1),
+             (20, 20, np.array([0, 3, 3, 10] + [10] * 17, np.int32), None, None),
+             (0, 0, np.zeros(1, np.int32), None, None)]
+    for m, n, rp, ci, v in cases:
+        for vs in (8, 4):
+            for nranks in (1, 2, 3, 4, 8):
+                want = sh.row_ranges(sh.partition(sh.block_row_weights(rp, m, vs), nranks), m) if m else [(0, 0)] * nranks
+                assert sh.partition_rows(rp, m, nranks, vs) == want, (m, vs, nranks)
+
+
 def test_partition_more_ranks_than_block_rows_and_ragged_tail():
     w = sh.block_row_weights(np.array([0, 3, 3, 10] + [10] * 17, np.int64), 20, 8)  # 20 rows -> 2 block rows
     parts = sh.partition(w, 4)

@@ -81,7 +81,7 @@ EXPORTS = [
     "tilespmv_convert", "tilespmv_dmat_upload_f64", "tilespmv_dmat_upload_f32",
     "tilespmv_dmat_export_f64", "tilespmv_dmat_export_f32", "tilespmv_dmat_destroy",
     "tilespmv_dmat_get_info", "tilespmv_plan_create", "tilespmv_plan_destroy", "tilespmv_plan_spmv",
-    "tilespmv_plan_spmv_host", "tilespmv_plan_spmv_host_batch", "tilespmv_plan_iterate", "tilespmv_plan_set_peers", "tilespmv_plan_get_info", "tilespmv_plan_time",
+    "tilespmv_plan_spmv_host", "tilespmv_plan_spmv_host_batch", "tilespmv_plan_iterate", "tilespmv_partition_rows", "tilespmv_plan_set_peers", "tilespmv_plan_get_info", "tilespmv_plan_time",
     "tilespmv_mmio_allinone_f64", "tilespmv_mmio_allinone_f32", "tilespmv_last_error",
     "tilespmv_version", "tilespmv_kernel_launch_count",
 ]
@@ -114,6 +114,7 @@ def load(rebuild=False):
     L.tilespmv_plan_spmv.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.tilespmv_plan_spmv_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.tilespmv_plan_spmv_host_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    L.tilespmv_partition_rows.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     L.tilespmv_plan_iterate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.tilespmv_plan_time.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                      C.POINTER(C.c_double)]

@@ -6,6 +6,7 @@
 #include <sys/time.h>
 
 #include <cctype>
+#include <cmath>
 #include <charconv>
 #include <new>
 
@@ -1136,6 +1137,41 @@ int tilespmv_plan_iterate(tilespmv_plan *plan, void *d_xa, void *d_xb, int niter
     tilespmv_plan_info info;
     tilespmv_plan_get_info(plan, &info);
     g_launches.fetch_add((int64_t)niters * info.launches_per_spmv, std::memory_order_relaxed);
+    return TILESPMV_OK;
+}
+
+int tilespmv_partition_rows(int precision, int rowA, const int *rowptr, int nparts, int *row_cuts)
+{
+    if ((precision != TILESPMV_F64 && precision != TILESPMV_F32) || rowA < 0 || nparts < 1 || !row_cuts || (rowA > 0 && !rowptr))
+    {
+        set_error("partition_rows: invalid argument");
+        return TILESPMV_ERR_INVALID;
+    }
+    // streamed bytes per block row with the weights of B_alg: value + 4-bit index per nonzero, 16 y
+    // values written, one row record; tile headers are not known before conversion and second order
+    const int tilem = (rowA + TS - 1) / TS;
+    std::vector<double> pre((size_t)tilem + 1, 0.0);
+    for (int b = 0; b < tilem; b++)
+    {
+        const int r0 = b * TS, r1 = std::min(rowA, r0 + TS);
+        const double nnz_br = (double)rowptr[r1] - (double)rowptr[r0];
+        pre[(size_t)b + 1] = pre[(size_t)b] + nnz_br * ((double)precision + 0.5) + (double)(TS * precision) + 16.0;
+    }
+    const double total = pre[(size_t)tilem];
+    int last = 0;
+    row_cuts[0] = 0;
+    for (int g = 1; g < nparts; g++)
+    {
+        // cut where the prefix crosses g / nparts of the total: the nearer of the two neighbouring block-row boundaries
+        const double target = total * (double)g / (double)nparts;
+        int b = (int)(std::lower_bound(pre.begin(), pre.end(), target) - pre.begin());
+        if (b > 0 && std::fabs(pre[(size_t)b - 1] - target) <= std::fabs(pre[(size_t)std::min(b, tilem)] - target))
+            b--;
+        b = std::min(std::max(b, last), tilem);
+        last = b;
+        row_cuts[g] = std::min(b * TS, rowA);
+    }
+    row_cuts[nparts] = rowA;
     return TILESPMV_OK;
 }
 

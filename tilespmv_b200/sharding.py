@@ -50,6 +50,18 @@ def row_ranges(parts, rowA):
     return [(min(b0 * TS, rowA), min(b1 * TS, rowA)) for b0, b1 in parts]
 
 
+def partition_rows(rowptr, rowA, nranks, value_bytes=8):
+    """The same cuts computed by the library (tilespmv_partition_rows, host-only C): row ranges per rank."""
+    import ctypes as C
+
+    from . import _capi
+    rp = np.ascontiguousarray(rowptr, np.int32)
+    cuts = np.zeros(nranks + 1, np.int32)
+    _capi.check(_capi.load().tilespmv_partition_rows(value_bytes, rowA, rp.ctypes.data_as(C.c_void_p), nranks,
+                                                     cuts.ctypes.data_as(C.c_void_p)), "tilespmv_partition_rows")
+    return [(int(cuts[i]), int(cuts[i + 1])) for i in range(nranks)]
+
+
 def imbalance(weights, parts):
     """max over ranks of shard weight / mean shard weight (1.0 = perfect)."""
     w = np.asarray(weights, np.float64)
