@@ -292,6 +292,64 @@ int tilespmv_partition_rows(int precision, int rowA, const int *rowptr, int npar
  */
 int tilespmv_plan_set_peers(tilespmv_plan *plan, int npeers, void *const *peer_x, int64_t row_offset);
 
+/* ============================ multi-GPU repeated SpMV (one process per GPU) ============================
+ *
+ * The reference is single-GPU (main.cu:74 selects one device).  This part implements what SURVEY.md 8b / 8e ask for:
+ * the matrix cut into contiguous row blocks (tilespmv_partition_rows), one rank = one process = one GPU of the box, x
+ * replicated, and the loop x <- A*x with the y slices all-gathered into the next x every iteration.  No torch, no MPI:
+ *
+ *   tilespmv_comm_create   rendezvous of the ranks through a POSIX shared-memory segment called `name` (all ranks pass
+ *                          the same name, unique per job; rank 0 creates it).  With TILESPMV_COMM_NCCL the library also
+ *                          creates an NCCL communicator (the unique id travels through the segment).
+ *   tilespmv_dist_create   collective over the communicator.  `local_rows` is THIS rank's shard (rows
+ *                          [row_cuts[rank], row_cuts[rank+1]) with GLOBAL column indices, converted with
+ *                          tilespmv_convert); row_cuts[nranks + 1] are the cuts of tilespmv_partition_rows.  Builds the
+ *                          rank's plan and two replicated x buffers that every peer maps through CUDA IPC (NVLink P2P).
+ *   tilespmv_dist_iterate  niters times x <- A*x, asynchronous on `stream`.  d_x0 = the replicated start vector (device
+ *                          pointer, colA values, the same on every rank) or NULL to continue from the current x.
+ *   tilespmv_dist_x        device pointer of the current replicated x (valid until the next iterate call).
+ *   tilespmv_dist_sync     waits for `stream` and the library's copy stream; reports a peer that never arrived (the
+ *                          device-side waits give up after TILESPMV_COMM_SPIN_TIMEOUT_S, default 30 s) as an error.
+ *
+ * Exchanges (all give bitwise identical x: the arithmetic is the same plan):
+ *   TILESPMV_EXCHANGE_NCCL       SpMV, then one in-place ncclAllGather (equal slices) or a grouped ncclBroadcast per rank
+ *   TILESPMV_EXCHANGE_FUSED      the SpMV kernel's epilogue stores y into every peer's next x over NVLink; one flag
+ *                                barrier per iteration
+ *   TILESPMV_EXCHANGE_PIPELINED  copy engines push the slice to the peers in the order they need it; every launch of the
+ *                                next iteration waits only for the slices its columns read (x panels cut at the row blocks
+ *                                of the ranks, own panel first), so the exchange runs under the next iteration's compute
+ * All ranks must make the same sequence of calls with the same niters / exchange.  A tilespmv_dist must be destroyed
+ * before its communicator (destroy is collective too).
+ */
+typedef struct tilespmv_comm tilespmv_comm;
+typedef struct tilespmv_dist tilespmv_dist;
+#define TILESPMV_COMM_NCCL 1u          /* flag of tilespmv_comm_create: also create an NCCL communicator */
+#define TILESPMV_DIST_UNIFORM_PANELS 1u /* flag of tilespmv_dist_create: keep the single-GPU x-panel cuts (no rank-aligned panels) */
+#define TILESPMV_EXCHANGE_NCCL 0
+#define TILESPMV_EXCHANGE_FUSED 1
+#define TILESPMV_EXCHANGE_PIPELINED 2
+int tilespmv_comm_create(const char *name, int rank, int nranks, unsigned flags, tilespmv_comm **out);
+void tilespmv_comm_destroy(tilespmv_comm *comm);
+int tilespmv_comm_barrier(tilespmv_comm *comm); /* host barrier over all ranks */
+int tilespmv_dist_create(tilespmv_comm *comm, const tilespmv_dmat *local_rows, const int64_t *row_cuts,
+                         const tilespmv_plan_options *opts, unsigned flags, tilespmv_dist **out);
+void tilespmv_dist_destroy(tilespmv_dist *dist);
+int tilespmv_dist_iterate(tilespmv_dist *dist, const void *d_x0, int niters, int exchange, void *stream);
+void *tilespmv_dist_x(tilespmv_dist *dist);
+tilespmv_plan *tilespmv_dist_plan(tilespmv_dist *dist); /* the rank's plan (borrowed): single SpMV, info */
+int tilespmv_dist_sync(tilespmv_dist *dist, void *stream);
+typedef struct
+{
+    int rank, nranks;
+    int64_t row0, rows;      /* this rank's row block                                              */
+    int64_t slice_bytes;     /* bytes of y this rank contributes to every all-gather               */
+    int64_t device_bytes;
+    int launch_units;        /* kernel launches per SpMV that can wait for different slices of x   */
+    int equal_slices;        /* all row blocks have the same length (NCCL: one ncclAllGather)      */
+    uint32_t unit_deps[64];  /* per launch unit: bit mask of the ranks whose slices of x it reads  */
+} tilespmv_dist_info;
+int tilespmv_dist_get_info(const tilespmv_dist *dist, tilespmv_dist_info *info);
+
 typedef struct
 {
     int precision;

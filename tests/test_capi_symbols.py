@@ -163,3 +163,24 @@ def test_mmio_parallel_parser_cache_and_fallback(tmp_path, monkeypatch):
     _same(second, ora.mtx_read(big)[1])
     rc, f32 = api.mmio_allinone(big, api.F32)
     assert rc == 0 and f32[5].dtype == np.float32 and len(list(cache.iterdir())) == 2
+
+
+def test_mmio_blank_lines_before_the_size_line(tmp_path):
+    """A blank / whitespace-only line between the comment block and the size line: the reference (mmio.h:600-612)
+    keeps reading lines until one yields three integers; the entries then start right after THAT line."""
+    from oracle import oracle_py as O
+    ora = O.Oracle("f64")
+    small = str(tmp_path / "blank_small.mtx")
+    with open(small, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n% comment\n\n   \n4 5 3\n1 1 1.5\n4 5 -2\n2 3 7\n")
+    big = str(tmp_path / "blank_big.mtx")
+    rng = np.random.default_rng(9)
+    with open(big, "w") as f:  # >= 4096 entries: the parallel parser
+        f.write("%%MatrixMarket matrix coordinate real general\n%c\n\n900 800 5000\n")
+        for _ in range(5000):
+            f.write(f"{rng.integers(1, 901)} {rng.integers(1, 801)} {rng.uniform(-1, 1):.17e}\n")
+    for p, nnz in ((small, 3), (big, 5000)):
+        rc, got = api.mmio_allinone(p)
+        rco, want = ora.mtx_read(p)
+        assert rc == rco == 0 and len(got[4]) == nnz
+        _same(got, want)

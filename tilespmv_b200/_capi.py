@@ -66,6 +66,17 @@ class PlanOptions(C.Structure):
                 ("stages", C.c_int), ("max_warps", C.c_int), ("flags", C.c_int), ("xpanel_bytes", C.c_int), ("reserved", C.c_int * 1)]
 
 
+class DistInfo(C.Structure):
+    _fields_ = [("rank", C.c_int), ("nranks", C.c_int), ("row0", C.c_int64), ("rows", C.c_int64),
+                ("slice_bytes", C.c_int64), ("device_bytes", C.c_int64), ("launch_units", C.c_int),
+                ("equal_slices", C.c_int), ("unit_deps", C.c_uint32 * 64)]
+
+
+COMM_NCCL = 1
+DIST_UNIFORM_PANELS = 1
+EXCHANGE_NCCL, EXCHANGE_FUSED, EXCHANGE_PIPELINED = 0, 1, 2
+
+
 class PlanInfo(C.Structure):
     _fields_ = [("precision", C.c_int), ("nchunks", C.c_int64), ("stream_bytes", C.c_int64),
                 ("algorithmic_bytes", C.c_int64), ("csr_bytes", C.c_int64), ("split_rows", C.c_int64),
@@ -84,6 +95,9 @@ EXPORTS = [
     "tilespmv_plan_spmv_host", "tilespmv_plan_spmv_host_batch", "tilespmv_plan_iterate", "tilespmv_partition_rows", "tilespmv_plan_set_peers", "tilespmv_plan_get_info", "tilespmv_plan_time",
     "tilespmv_mmio_allinone_f64", "tilespmv_mmio_allinone_f32", "tilespmv_last_error",
     "tilespmv_version", "tilespmv_kernel_launch_count",
+    "tilespmv_comm_create", "tilespmv_comm_destroy", "tilespmv_comm_barrier", "tilespmv_dist_create",
+    "tilespmv_dist_destroy", "tilespmv_dist_iterate", "tilespmv_dist_x", "tilespmv_dist_plan", "tilespmv_dist_sync",
+    "tilespmv_dist_get_info",
 ]
 
 _lib = None
@@ -99,10 +113,12 @@ def load(rebuild=False):
     if _lib is not None and not rebuild:
         return _lib
     path = build.LIB_CUDA
-    if rebuild or not os.path.exists(path):
-        build.build_cuda()
+    # build_cuda() is a no-op unless a source is newer than the .so: a stale binary whose struct layouts differ from
+    # the ctypes mirrors below must never be loaded silently
+    build.build_cuda(force=rebuild)
     if not os.path.exists(path):
         raise RuntimeError("libtilespmv_b200.so is missing and could not be built; there is no CPU fallback")
+    _preload_nccl()
     L = C.CDLL(path)
     L.tilespmv_last_error.restype = C.c_char_p
     L.tilespmv_version.restype = C.c_char_p
@@ -130,8 +146,39 @@ def load(rebuild=False):
     L.tilespmv_dmat_export_f32.argtypes = [C.c_void_p, C.POINTER(TileMatrixF32)]
     L.tilespmv_dmat_upload_f64.argtypes = [C.POINTER(TileMatrixF64), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.tilespmv_dmat_upload_f32.argtypes = [C.POINTER(TileMatrixF32), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.tilespmv_comm_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_uint, C.POINTER(C.c_void_p)]
+    L.tilespmv_comm_destroy.argtypes = [C.c_void_p]
+    L.tilespmv_comm_destroy.restype = None
+    L.tilespmv_comm_barrier.argtypes = [C.c_void_p]
+    L.tilespmv_dist_create.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(PlanOptions), C.c_uint,
+                                       C.POINTER(C.c_void_p)]
+    L.tilespmv_dist_destroy.argtypes = [C.c_void_p]
+    L.tilespmv_dist_destroy.restype = None
+    L.tilespmv_dist_iterate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.tilespmv_dist_x.argtypes = [C.c_void_p]
+    L.tilespmv_dist_x.restype = C.c_void_p
+    L.tilespmv_dist_plan.argtypes = [C.c_void_p]
+    L.tilespmv_dist_plan.restype = C.c_void_p
+    L.tilespmv_dist_sync.argtypes = [C.c_void_p, C.c_void_p]
+    L.tilespmv_dist_get_info.argtypes = [C.c_void_p, C.POINTER(DistInfo)]
     _lib = L
     return L
+
+
+def _preload_nccl():
+    """libtilespmv_b200.so links libnccl.so.2.  In a process that also runs torch the SAME NCCL must serve both, and
+    torch ships its own (newer) copy: load that one first so the library's DT_NEEDED resolves to it whatever the
+    import order.  A plain C host simply gets the system libnccl."""
+    import glob
+    import sysconfig
+    for base in {sysconfig.get_paths()["purelib"], sysconfig.get_paths()["platlib"]}:
+        for so in glob.glob(os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.2")):
+            try:
+                C.CDLL(so, mode=C.RTLD_GLOBAL)
+                return so
+            except OSError:
+                pass
+    return None
 
 
 class TileSpMVError(RuntimeError):

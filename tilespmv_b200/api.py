@@ -107,8 +107,8 @@ def call_tilespmv_cuda(filename, M, rowA, colA, nnzA, x, alpha=1.0):
     fn = L.call_tilespmv_cuda_f64 if M.precision == F64 else L.call_tilespmv_cuda_f32
     fn(C.c_char_p(filename.encode()), C.byref(M.struct), null, null, C.c_int(0), null, null, null,
        C.c_int(rowA), C.c_int(colA), C.c_int(nnzA), null, null, null, vt(alpha), _ptr(x), _ptr(y), null)
-    err = L.tilespmv_last_error().decode()
-    if err.startswith("call_tilespmv_cuda"):
+    err = L.tilespmv_last_error().decode()  # the entry clears the error string first: anything left is this call's
+    if err:
         raise TileSpMVError(err)
     return y
 

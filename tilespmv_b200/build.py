@@ -25,11 +25,36 @@ NVCC_FLAGS = [
 ]
 
 
-def _stale(target, sources):
+# NCCL: the communicator of the multi-GPU repeated-SpMV loop lives inside the library (csrc/comm.cu)
+LINK_LIBS = ["-lcudart", "-lnccl", "-lgomp", "-lrt", "-lpthread"]
+
+
+def _digest(sources, flags):
+    """Content hash of the sources + the command line (mtimes do not survive a snapshot copy to the GPU box)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(flags).encode())
+    for s in sorted(sources):
+        h.update(os.path.basename(s).encode())
+        with open(s, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _stale(target, sources, flags=()):
+    """True when `target` is missing or was built from other sources / flags than the current ones (the digest of what
+    it was built from sits next to it in <target>.srchash, git-ignored like the .so itself)."""
     if not os.path.exists(target):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(s) > t for s in sources)
+    try:
+        with open(target + ".srchash") as f:
+            return f.read().strip() != _digest(sources, flags)
+    except OSError:
+        return True
+
+
+def _stamp(target, sources, flags=()):
+    with open(target + ".srchash", "w") as f:
+        f.write(_digest(sources, flags))
 
 
 def cuda_sources():
@@ -44,20 +69,45 @@ def cuda_deps():
 
 def build_gen(force=False, verbose=False):
     src = os.path.join(CSRC, "gen.c")
-    if force or _stale(LIB_GEN, [src]):
-        cmd = [GCC, "-O3", "-fopenmp", "-fPIC", "-shared", src, "-o", LIB_GEN]
+    flags = ["-O3", "-fopenmp", "-fPIC", "-shared"]
+    if force or _stale(LIB_GEN, [src], flags):
+        cmd = [GCC] + flags + [src, "-o", LIB_GEN]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
+        _stamp(LIB_GEN, [src], flags)
     return LIB_GEN
 
 
 def build_cuda(force=False, verbose=False, extra=()):
-    if force or _stale(LIB_CUDA, cuda_deps()):
-        cmd = [NVCC] + NVCC_FLAGS + list(extra) + cuda_sources() + ["-o", LIB_CUDA, "-lcudart", "-lgomp"]
-        if verbose:
-            print(" ".join(cmd))
-        subprocess.check_call(cmd)
+    """Every .cu is compiled to its own object (in parallel, only when its sources or flags changed) and the objects are
+    linked into libtilespmv_b200.so; nothing device-side crosses translation units, so no -rdc."""
+    flags = NVCC_FLAGS + list(extra) + LINK_LIBS
+    if not (force or _stale(LIB_CUDA, cuda_deps(), flags)):
+        return LIB_CUDA
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(PKG, "build")
+    os.makedirs(objdir, exist_ok=True)
+    headers = [d for d in cuda_deps() if not d.endswith(".cu")]
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + list(extra)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if force or _stale(obj, [src] + headers, cflags):
+            cmd = [NVCC] + cflags + ["-c", src, "-o", obj]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            subprocess.check_call(cmd)
+            _stamp(obj, [src] + headers, cflags)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, cuda_sources()))
+    cmd = [NVCC, "-shared", "-ccbin", GPP] + objs + ["-o", LIB_CUDA] + LINK_LIBS
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    _stamp(LIB_CUDA, cuda_deps(), flags)
     return LIB_CUDA
 
 

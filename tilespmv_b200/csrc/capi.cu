@@ -28,6 +28,7 @@ void set_error(const char *fmt, ...)
     g_error = buf;
 }
 const char *last_error() { return g_error.c_str(); }
+void clear_error() { g_error.clear(); }
 
 int require_device()
 {
@@ -231,7 +232,28 @@ static int dmat_upload(const TM *m, int rowA, int colA, tilespmv_dmat **out)
     UP(Blockell_Val, m->ellsize, T);
     UP(ell_compressedIdx, (m->ellsize + 1) / 2, unsigned char);
     UP(Blockhyb_Val, m->hybellsize + m->hybcoosize, T);
-    UP(hybIdx, (m->hybellsize + 1) / 2 + m->hybcoosize, unsigned char);
+    // hybIdx is indexed tile by tile with per-tile rounding (convert.cu, plan.cu TC_HYB_IDXBYTES), which can be up to
+    // one byte per HYB tile longer than the reference's length ceil(hybellsize/2) + hybcoosize (csr2tile.h:840-841;
+    // the reference overruns its own array there): allocate that slack zero-filled so the packer never reads past
+    // the buffer of an exported / reference-built struct
+    if (rc == TILESPMV_OK)
+    {
+        const size_t ref_len = ((size_t)m->hybellsize + 1) / 2 + (size_t)m->hybcoosize;
+        rc = d->hybIdx.alloc(ref_len + (size_t)d->fmt_hist[TILESPMV_FMT_HYB] + 16, true);
+        if (rc == TILESPMV_OK && ref_len)
+        {
+            if (!m->hybIdx)
+            {
+                set_error("upload: null array in Tile_matrix");
+                rc = TILESPMV_ERR_INVALID;
+            }
+            else if (cudaMemcpy(d->hybIdx.p, m->hybIdx, ref_len, cudaMemcpyHostToDevice) != cudaSuccess)
+            {
+                set_error("upload: H2D of hybIdx failed");
+                rc = TILESPMV_ERR_CUDA;
+            }
+        }
+    }
     UP(Blockdense_Val, m->dnssize, T);
     UP(Blockdenserow_Val, m->dnsrowsize, T);
     UP(denserowid, d->ndenserowid, char);
@@ -492,6 +514,10 @@ static void call_entry(char *filename, TM *matrix, int rowA, int colA, int nnzA,
     tilespmv_dmat *d = nullptr;
     tilespmv_plan *P = nullptr;
     auto fail = [&]() {
+        // whatever failed underneath (upload, plan, allocation), the caller sees it under this entry's name
+        const std::string why = last_error();
+        if (why.rfind("call_tilespmv_cuda", 0) != 0)
+            set_error("call_tilespmv_cuda: %s", why.c_str());
         fprintf(stderr, "call_tilespmv_cuda failed: %s\n", last_error());
         if (P)
             tilespmv_plan_destroy(P);
@@ -645,18 +671,33 @@ static int mmio_entry(int *m, int *n, int *nnz, int *isSymmetric, int **csrRowPt
     long M_ = 0, N_ = 0, NZ = 0;
     for (;;)
     {
+        // the size line: three integers on ONE line (mmio.h:600-612 reads line by line until sscanf yields 3 items);
+        // blank or malformed lines before it are skipped, and p always ends up right behind the size line itself
         if (p >= end)
             return -4;
-        char *e1;
-        M_ = strtol(p, &e1, 10);
-        char *e2;
-        N_ = strtol(e1, &e2, 10);
-        char *e3;
-        NZ = strtol(e2, &e3, 10);
-        bool ok = e1 != p && e2 != e1 && e3 != e2;
-        p = next_line(p);
-        if (ok)
+        const char *le = next_line(p);
+        const char *q = p;
+        long v3[3] = {0, 0, 0};
+        int got3 = 0;
+        for (; got3 < 3; got3++)
+        {
+            while (q < le && (*q == ' ' || *q == '\t'))
+                q++;
+            if (q < le && *q == '+')
+                q++;
+            auto r = std::from_chars(q, le, v3[got3]);
+            if (r.ec != std::errc())
+                break;
+            q = r.ptr;
+        }
+        p = le;
+        if (got3 == 3)
+        {
+            M_ = v3[0];
+            N_ = v3[1];
+            NZ = v3[2];
             break;
+        }
     }
     if (M_ < 0 || N_ < 0 || NZ < 0 || M_ > 0x7ffffff0l || N_ > 0x7ffffff0l || NZ > 0x7ffffff0l)
         return -4;
@@ -882,11 +923,13 @@ int64_t tilespmv_kernel_launch_count(void) { return g_launches.load(); }
 
 void Tile_create_f64(Tile_matrix_f64 *matrix, int rowA, int colA, int nnzA, int *csrRowPtrA, int *csrColIdxA, double *csrValA)
 {
+    clear_error();
     (void)nnzA;
     tile_create_entry<Tile_matrix_f64, double>(matrix, rowA, colA, csrRowPtrA, csrColIdxA, csrValA);
 }
 void Tile_create_f32(Tile_matrix_f32 *matrix, int rowA, int colA, int nnzA, int *csrRowPtrA, int *csrColIdxA, float *csrValA)
 {
+    clear_error();
     (void)nnzA;
     tile_create_entry<Tile_matrix_f32, float>(matrix, rowA, colA, csrRowPtrA, csrColIdxA, csrValA);
 }
@@ -897,6 +940,7 @@ int tilespmv_prepare_f64(const Tile_matrix_f64 *matrix, int *ptroffset1, int *pt
                          unsigned int **blkcoostylerowidx, int **blkcoostylerowidx_colstart,
                          int **blkcoostylerowidx_colstop, int rowA)
 {
+    clear_error();
     return prepare_entry(matrix, ptroffset1, ptroffset2, rowblkblock, blkcoostylerowidx, blkcoostylerowidx_colstart,
                          blkcoostylerowidx_colstop, rowA);
 }
@@ -904,6 +948,7 @@ int tilespmv_prepare_f32(const Tile_matrix_f32 *matrix, int *ptroffset1, int *pt
                          unsigned int **blkcoostylerowidx, int **blkcoostylerowidx_colstart,
                          int **blkcoostylerowidx_colstop, int rowA)
 {
+    clear_error();
     return prepare_entry(matrix, ptroffset1, ptroffset2, rowblkblock, blkcoostylerowidx, blkcoostylerowidx_colstart,
                          blkcoostylerowidx_colstop, rowA);
 }
@@ -911,39 +956,47 @@ int tilespmv_prepare_f32(const Tile_matrix_f32 *matrix, int *ptroffset1, int *pt
 void call_tilespmv_cuda_f64(char *filename, Tile_matrix_f64 *matrix, int *, int *, int, unsigned int *, int *, int *,
                             int rowA, int colA, int nnzA, int *, int *, double *, double, double *x, double *y, double *)
 {
+    clear_error();
     call_entry<Tile_matrix_f64, double>(filename, matrix, rowA, colA, nnzA, x, y);
 }
 void call_tilespmv_cuda_f32(char *filename, Tile_matrix_f32 *matrix, int *, int *, int, unsigned int *, int *, int *,
                             int rowA, int colA, int nnzA, int *, int *, float *, float, float *x, float *y, float *)
 {
+    clear_error();
     call_entry<Tile_matrix_f32, float>(filename, matrix, rowA, colA, nnzA, x, y);
 }
 
 int tilespmv_convert(int precision, int rowA, int colA, const int *rowptr, const int *colidx, const void *val,
                      unsigned flags, tilespmv_dmat **out)
 {
+    clear_error();
     return convert_entry(precision, rowA, colA, rowptr, colidx, val, flags, out);
 }
 int tilespmv_dmat_upload_f64(const Tile_matrix_f64 *matrix, int rowA, int colA, tilespmv_dmat **out)
 {
+    clear_error();
     return dmat_upload<Tile_matrix_f64, double>(matrix, rowA, colA, out);
 }
 int tilespmv_dmat_upload_f32(const Tile_matrix_f32 *matrix, int rowA, int colA, tilespmv_dmat **out)
 {
+    clear_error();
     return dmat_upload<Tile_matrix_f32, float>(matrix, rowA, colA, out);
 }
 int tilespmv_dmat_export_f64(const tilespmv_dmat *dm, Tile_matrix_f64 *matrix)
 {
+    clear_error();
     return dmat_export<Tile_matrix_f64, double>(dm, matrix);
 }
 int tilespmv_dmat_export_f32(const tilespmv_dmat *dm, Tile_matrix_f32 *matrix)
 {
+    clear_error();
     return dmat_export<Tile_matrix_f32, float>(dm, matrix);
 }
 void tilespmv_dmat_destroy(tilespmv_dmat *dm) { delete dm; }
 
 int tilespmv_dmat_get_info(const tilespmv_dmat *dm, tilespmv_dmat_info *info)
 {
+    clear_error();
     if (!dm || !info)
     {
         set_error("dmat_get_info: null argument");
@@ -971,6 +1024,7 @@ int tilespmv_dmat_get_info(const tilespmv_dmat *dm, tilespmv_dmat_info *info)
 
 int tilespmv_plan_create(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tilespmv_plan **out)
 {
+    clear_error();
     if (!dm || !out)
     {
         set_error("plan_create: null argument");
@@ -993,6 +1047,7 @@ void tilespmv_plan_destroy(tilespmv_plan *plan) { delete plan; }
 
 int tilespmv_plan_spmv(tilespmv_plan *plan, const void *d_x, void *d_y, void *stream)
 {
+    clear_error();
     if (!plan || (!d_x && plan->colA) || (!d_y && plan->rowA))
     {
         set_error("plan_spmv: null argument");
@@ -1003,6 +1058,7 @@ int tilespmv_plan_spmv(tilespmv_plan *plan, const void *d_x, void *d_y, void *st
 
 int tilespmv_plan_spmv_host(tilespmv_plan *plan, const void *x, void *y)
 {
+    clear_error();
     if (!plan || (!x && plan->colA) || (!y && plan->rowA))
     {
         set_error("plan_spmv_host: null argument");
@@ -1024,6 +1080,7 @@ int tilespmv_plan_spmv_host(tilespmv_plan *plan, const void *x, void *y)
 
 int tilespmv_plan_spmv_host_batch(tilespmv_plan *plan, int nvec, const void *const *x, void *const *y)
 {
+    clear_error();
     if (!plan || nvec < 0 || (nvec > 0 && (!x || !y)))
     {
         set_error("plan_spmv_host_batch: invalid argument");
@@ -1031,19 +1088,31 @@ int tilespmv_plan_spmv_host_batch(tilespmv_plan *plan, int nvec, const void *con
     }
     constexpr int R = tilespmv_plan::HOST_RING;
     const size_t xb = (size_t)plan->colA * (size_t)plan->precision, yb = (size_t)plan->rowA * (size_t)plan->precision;
-    if (!plan->s_in)
+    if (!plan->ring_ready)
     {
-        TSP_CUDA(cudaStreamCreateWithFlags(&plan->s_in, cudaStreamNonBlocking));
-        TSP_CUDA(cudaStreamCreateWithFlags(&plan->s_comp, cudaStreamNonBlocking));
-        TSP_CUDA(cudaStreamCreateWithFlags(&plan->s_out, cudaStreamNonBlocking));
-        for (int i = 0; i < R; i++)
+        // streams, events and buffers are created as a unit: a failure half-way tears everything down again so that
+        // the next call starts from scratch instead of launching on null buffers
+        auto setup = [&]() -> int {
+            TSP_CUDA(cudaStreamCreateWithFlags(&plan->s_in, cudaStreamNonBlocking));
+            TSP_CUDA(cudaStreamCreateWithFlags(&plan->s_comp, cudaStreamNonBlocking));
+            TSP_CUDA(cudaStreamCreateWithFlags(&plan->s_out, cudaStreamNonBlocking));
+            for (int i = 0; i < R; i++)
+            {
+                TSP_CUDA(cudaEventCreateWithFlags(&plan->ev_in[i], cudaEventDisableTiming));
+                TSP_CUDA(cudaEventCreateWithFlags(&plan->ev_comp[i], cudaEventDisableTiming));
+                TSP_CUDA(cudaEventCreateWithFlags(&plan->ev_out[i], cudaEventDisableTiming));
+                TSP_TRY(plan->bx[i].alloc(xb, false));
+                TSP_TRY(plan->by[i].alloc(yb, false)); // not zeroed: the plan writes every row (and a memset on the legacy stream would race with s_comp)
+            }
+            return TILESPMV_OK;
+        };
+        const int rc = setup();
+        if (rc != TILESPMV_OK)
         {
-            TSP_CUDA(cudaEventCreateWithFlags(&plan->ev_in[i], cudaEventDisableTiming));
-            TSP_CUDA(cudaEventCreateWithFlags(&plan->ev_comp[i], cudaEventDisableTiming));
-            TSP_CUDA(cudaEventCreateWithFlags(&plan->ev_out[i], cudaEventDisableTiming));
-            TSP_TRY(plan->bx[i].alloc(xb, false));
-            TSP_TRY(plan->by[i].alloc(yb, true));
+            plan->release_host_ring();
+            return rc;
         }
+        plan->ring_ready = true;
     }
     // vector i uses ring slot i % R.  H2D stream: x_i -> bx once the kernel that last read bx is done; kernel
     // stream: SpMV once x_i has landed and the D2H that last read by is done; D2H stream: by -> y_i.  The two
@@ -1079,6 +1148,7 @@ int tilespmv_plan_spmv_host_batch(tilespmv_plan *plan, int nvec, const void *con
 
 int tilespmv_plan_iterate(tilespmv_plan *plan, void *d_xa, void *d_xb, int niters, void *stream)
 {
+    clear_error();
     if (!plan || niters < 0 || ((!d_xa || !d_xb) && plan->rowA))
     {
         set_error("plan_iterate: invalid argument");
@@ -1142,6 +1212,7 @@ int tilespmv_plan_iterate(tilespmv_plan *plan, void *d_xa, void *d_xb, int niter
 
 int tilespmv_partition_rows(int precision, int rowA, const int *rowptr, int nparts, int *row_cuts)
 {
+    clear_error();
     if ((precision != TILESPMV_F64 && precision != TILESPMV_F32) || rowA < 0 || nparts < 1 || !row_cuts || (rowA > 0 && !rowptr))
     {
         set_error("partition_rows: invalid argument");
@@ -1177,6 +1248,7 @@ int tilespmv_partition_rows(int precision, int rowA, const int *rowptr, int npar
 
 int tilespmv_plan_set_peers(tilespmv_plan *plan, int npeers, void *const *peer_x, int64_t row_offset)
 {
+    clear_error();
     if (!plan || npeers < 0 || npeers > TSP_MAX_PEERS || (npeers > 0 && !peer_x))
     {
         set_error("plan_set_peers: invalid argument (at most %d peers)", TSP_MAX_PEERS);
@@ -1191,6 +1263,7 @@ int tilespmv_plan_set_peers(tilespmv_plan *plan, int npeers, void *const *peer_x
 
 int tilespmv_plan_get_info(const tilespmv_plan *plan, tilespmv_plan_info *info)
 {
+    clear_error();
     if (!plan || !info)
     {
         set_error("plan_get_info: null argument");
@@ -1228,6 +1301,7 @@ int tilespmv_plan_get_info(const tilespmv_plan *plan, tilespmv_plan_info *info)
 int tilespmv_plan_time(tilespmv_plan *plan, const void *d_x, void *d_y, int warmup, int iters, void *stream,
                        double *ms_per_spmv)
 {
+    clear_error();
     if (!plan || !ms_per_spmv)
     {
         set_error("plan_time: null argument");
@@ -1239,11 +1313,13 @@ int tilespmv_plan_time(tilespmv_plan *plan, const void *d_x, void *d_y, int warm
 int tilespmv_mmio_allinone_f64(int *m, int *n, int *nnz, int *isSymmetric, int **csrRowPtr, int **csrColIdx,
                                double **csrVal, const char *filename)
 {
+    clear_error();
     return mmio_entry<double>(m, n, nnz, isSymmetric, csrRowPtr, csrColIdx, csrVal, filename);
 }
 int tilespmv_mmio_allinone_f32(int *m, int *n, int *nnz, int *isSymmetric, int **csrRowPtr, int **csrColIdx,
                                float **csrVal, const char *filename)
 {
+    clear_error();
     return mmio_entry<float>(m, n, nnz, isSymmetric, csrRowPtr, csrColIdx, csrVal, filename);
 }
 

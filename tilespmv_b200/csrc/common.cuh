@@ -23,6 +23,7 @@ constexpr int TS = TILESPMV_BLOCK_SIZE; // 16 x 16 tiles (common.h:37-39 of the 
 // ---------------------------------------------------------------------------------------------
 void set_error(const char *fmt, ...);
 const char *last_error();
+void clear_error(); // every extern "C" entry starts with a clean error string (a stale message must not outlive a later success)
 extern std::atomic<int64_t> g_launches;
 
 struct Status

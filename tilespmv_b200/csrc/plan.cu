@@ -1198,7 +1198,7 @@ struct PanelCountIn // flattened [P][rowA + 1]: entries of (panel, row); the las
 {
     const int *side_ptr, *side_col;
     int rowA, npanels;
-    long long panel_cols;
+    const long long *cuts; // [npanels + 1] ascending column cuts; panel p = columns [cuts[p], cuts[p+1])
     __device__ __forceinline__ int operator()(size_t k) const
     {
         const size_t stride = (size_t)rowA + 1;
@@ -1208,12 +1208,12 @@ struct PanelCountIn // flattened [P][rowA + 1]: entries of (panel, row); the las
         if (i >= rowA)
             return 0;
         const int lo = side_ptr[i], hi = side_ptr[i + 1];
-        return lower_bound_col(side_col, lo, hi, (long long)(p + 1) * panel_cols) - lower_bound_col(side_col, lo, hi, (long long)p * panel_cols);
+        return lower_bound_col(side_col, lo, hi, cuts[p + 1]) - lower_bound_col(side_col, lo, hi, cuts[p]);
     }
 };
 template <class T>
 __global__ void __launch_bounds__(PL_THREADS)
-    panel_scatter_kernel(int rowA, int npanels, long long panel_cols, const int *__restrict__ side_ptr,
+    panel_scatter_kernel(int rowA, int npanels, const long long *__restrict__ cuts, const int *__restrict__ side_ptr,
                          const int *__restrict__ side_col, const T *__restrict__ side_val, const int *__restrict__ ptr2,
                          int *__restrict__ col2, T *__restrict__ val2)
 {
@@ -1221,10 +1221,10 @@ __global__ void __launch_bounds__(PL_THREADS)
     if (i >= rowA)
         return;
     const int lo = side_ptr[i], hi = side_ptr[i + 1];
-    int q = lo;
+    int q = lower_bound_col(side_col, lo, hi, cuts[0]);
     for (int p = 0; p < npanels && q < hi; p++)
     {
-        const int e = lower_bound_col(side_col, q, hi, (long long)(p + 1) * panel_cols);
+        const int e = lower_bound_col(side_col, q, hi, cuts[p + 1]);
         int dst = ptr2[(size_t)p * ((size_t)rowA + 1) + i];
         for (; q < e; q++, dst++)
         {
@@ -1234,33 +1234,94 @@ __global__ void __launch_bounds__(PL_THREADS)
     }
 }
 
-template <class T>
-static int plan_build_panels(const tilespmv_dmat *dm, tilespmv_plan *P, int npanels, long long panel_cols, cudaStream_t s)
+// smallest / largest x column a plan source reads: tile columns of the stream tiles (COO tiles live in the side
+// matrix) and the global columns of the side entries.  out = {min, max} (INT_MAX / -1 when nothing is read).
+__global__ void __launch_bounds__(PL_THREADS)
+    col_range_kernel(long long ntiles, const int *__restrict__ tile_columnidx, const char *__restrict__ Format,
+                     long long nside, const int *__restrict__ side_col, int *__restrict__ out)
 {
-    const int rowA = dm->rowA;
+    int lo = 0x7fffffff, hi = -1;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += stride)
+        if (Format[t] != TILESPMV_FMT_COO)
+        {
+            const int c = tile_columnidx[t] * TS;
+            lo = min(lo, c);
+            hi = max(hi, c + TS - 1);
+        }
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nside; e += stride)
+    {
+        const int c = side_col[e];
+        lo = min(lo, c);
+        hi = max(hi, c);
+    }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        if (lo != 0x7fffffff)
+            atomicMin(out, lo);
+        if (hi >= 0)
+            atomicMax(out + 1, hi);
+    }
+}
+
+// records [xcol_lo, xcol_hi) of a (sub-)plan: which part of x its launch reads (drives the per-launch dependencies
+// of the pipelined multi-GPU exchange, comm.cu)
+static int plan_col_range(const tilespmv_dmat *dm, bool tiles, const int *side_col, long long nside, tilespmv_plan *P, cudaStream_t s)
+{
+    DevBuf d;
+    TSP_TRY(d.alloc(2 * sizeof(int), false));
+    const int init[2] = {0x7fffffff, -1};
+    TSP_CUDA(cudaMemcpyAsync(d.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
+    const long long nt = tiles ? dm->tilenum : 0;
+    if (nt + nside > 0)
+        TSP_LAUNCH(col_range_kernel, std::min<unsigned>(grid_for((size_t)std::max(nt, nside), PL_THREADS), 2048u), PL_THREADS, 0, s, nt,
+                   dm->tile_columnidx.as<int>(), dm->Format.as<char>(), nside, side_col, d.as<int>());
+    int h[2];
+    TSP_CUDA(cudaMemcpyAsync(h, d.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    TSP_CUDA(cudaStreamSynchronize(s));
+    P->xcol_lo = h[1] >= 0 ? h[0] : 0;
+    P->xcol_hi = h[1] >= 0 ? std::min<long long>((long long)h[1] + 1, dm->colA) : 0;
+    return TILESPMV_OK;
+}
+
+// cuts[npanels + 1]: ascending column cuts (cuts[0] = 0, cuts[npanels] >= colA); order[npanels]: the launch order of the
+// panels.  The plan itself takes the tiles + panel order[0] and WRITES y; sub[i-1] takes panel order[i] and accumulates.
+template <class T>
+static int plan_build_panels(const tilespmv_dmat *dm, tilespmv_plan *P, const std::vector<long long> &cuts,
+                             const std::vector<int> &order, cudaStream_t s)
+{
+    const int rowA = dm->rowA, npanels = (int)order.size();
     const size_t stride = (size_t)rowA + 1, flat = stride * (size_t)npanels;
     ScanWorkspace ws;
-    DevBuf ptr2, col2, val2, zeros;
+    DevBuf ptr2, col2, val2, zeros, d_cuts;
     TSP_TRY(ptr2.alloc((flat + 1) * sizeof(int), false));
     TSP_TRY(col2.alloc((size_t)dm->coototal * sizeof(int), false));
     TSP_TRY(val2.alloc((size_t)dm->coototal * sizeof(T), false));
     TSP_TRY(zeros.alloc(((size_t)dm->tilem + 1) * sizeof(int), true, s));
+    TSP_TRY(d_cuts.alloc(cuts.size() * sizeof(long long), false));
+    TSP_CUDA(cudaMemcpyAsync(d_cuts.p, cuts.data(), cuts.size() * sizeof(long long), cudaMemcpyHostToDevice, s));
     long long total = 0;
-    PanelCountIn in{dm->deferredcoo_ptr.as<int>(), dm->deferredcoo_colidx.as<int>(), rowA, npanels, panel_cols};
+    PanelCountIn in{dm->deferredcoo_ptr.as<int>(), dm->deferredcoo_colidx.as<int>(), rowA, npanels, d_cuts.as<long long>()};
     TSP_TRY(exclusive_scan(in, flat + 1, ptr2.as<int>(), ws, s, &total));
     if (total != (long long)dm->coototal)
     {
         set_error("plan: x-panel split lost entries (%lld of %d)", total, dm->coototal);
         return TILESPMV_ERR_CUDA;
     }
-    TSP_LAUNCH((panel_scatter_kernel<T>), grid_for((size_t)rowA, PL_THREADS), PL_THREADS, 0, s, rowA, npanels, panel_cols,
+    TSP_LAUNCH((panel_scatter_kernel<T>), grid_for((size_t)rowA, PL_THREADS), PL_THREADS, 0, s, rowA, npanels, d_cuts.as<long long>(),
                dm->deferredcoo_ptr.as<int>(), dm->deferredcoo_colidx.as<int>(), dm->deferredcoo_val.as<T>(), ptr2.as<int>(),
                col2.as<int>(), val2.as<T>());
     const int user_chunk = P->chunk_bytes, user_xstage = P->xstage_bytes;
-    for (int p = 0; p < npanels; p++)
+    for (int i = 0; i < npanels; i++)
     {
+        const int p = order[(size_t)i];
         tilespmv_plan *Q = P;
-        if (p > 0)
+        if (i > 0)
         {
             Q = new (std::nothrow) tilespmv_plan();
             if (!Q)
@@ -1278,17 +1339,49 @@ static int plan_build_panels(const tilespmv_dmat *dm, tilespmv_plan *P, int npan
             Q->chunk_bytes = user_chunk;
             Q->xstage_bytes = user_xstage;
             Q->accumulate = true;
-            Q->keep_all_rows = p == npanels - 1; // the last panel visits every row: it carries the fused peer stores
+            Q->keep_all_rows = i == npanels - 1; // the last launch visits every row: it carries the fused peer stores
         }
-        PlanSource src{p == 0, p == 0 ? dm->tile_ptr.as<int>() : zeros.as<int>(), ptr2.as<int>() + (size_t)p * stride, col2.as<int>(),
+        PlanSource src{i == 0, i == 0 ? dm->tile_ptr.as<int>() : zeros.as<int>(), ptr2.as<int>() + (size_t)p * stride, col2.as<int>(),
                        val2.p};
         TSP_TRY(plan_build_t<T>(dm, src, Q, s));
+        // the part of x this launch reads: its panel (clipped to colA), widened by the tile columns for the first one
+        Q->xcol_lo = std::min<long long>(cuts[(size_t)p], dm->colA);
+        Q->xcol_hi = std::min<long long>(cuts[(size_t)p + 1], dm->colA);
+        if (i == 0 && dm->tilenum > dm->fmt_hist[TILESPMV_FMT_COO])
+        {
+            tilespmv_plan tmp;
+            TSP_TRY(plan_col_range(dm, true, nullptr, 0, &tmp, s));
+            if (tmp.xcol_hi > tmp.xcol_lo)
+            {
+                Q->xcol_lo = std::min(Q->xcol_lo, tmp.xcol_lo);
+                Q->xcol_hi = std::max(Q->xcol_hi, tmp.xcol_hi);
+            }
+        }
     }
     TSP_CUDA(cudaStreamSynchronize(s));
     return TILESPMV_OK;
 }
 
-int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tilespmv_plan *P, cudaStream_t s)
+// x panels (plan.cuh): automatic when x is larger than L2 (panels of half of L2) and at least a quarter of the nonzeros are
+// side entries (random gathers); xpanel_bytes > 0 forces that panel width, < 0 switches panels off.  *out = 0: no panels.
+int plan_panel_bytes(const tilespmv_dmat *dm, int xpanel_bytes, long long *out)
+{
+    *out = 0;
+    if (xpanel_bytes > 0)
+        *out = xpanel_bytes;
+    else if (xpanel_bytes == 0 && dm->coototal > 0 && (int64_t)dm->coototal * 4 >= dm->nnz)
+    {
+        int dev = 0, l2 = 0;
+        TSP_CUDA(cudaGetDevice(&dev));
+        TSP_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
+        const long long budget = (long long)l2 / 2; // config-5 shard: 33 MB panels 1.32 ms, 50 MB 1.08, 67 MB 1.06, 100 MB 1.25
+        if ((long long)dm->colA * dm->precision > 2 * budget)
+            *out = budget;
+    }
+    return TILESPMV_OK;
+}
+
+int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tilespmv_plan *P, cudaStream_t s, const PanelSpec *spec)
 {
     P->precision = dm->precision;
     P->rowA = dm->rowA;
@@ -1312,25 +1405,41 @@ int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tiles
                   16 * vs);
         return TILESPMV_ERR_INVALID;
     }
-    // x panels (plan.cuh): automatic when x is larger than L2 (panels of half of L2) and at least a quarter of the nonzeros are
-    // side entries (random gathers); xpanel_bytes > 0 forces that panel width, < 0 switches panels off
     long long panel_bytes = 0;
-    if (P->xpanel_bytes > 0)
-        panel_bytes = P->xpanel_bytes;
-    else if (P->xpanel_bytes == 0 && dm->coototal > 0 && (int64_t)dm->coototal * 4 >= dm->nnz)
+    TSP_TRY(plan_panel_bytes(dm, P->xpanel_bytes, &panel_bytes));
+    std::vector<long long> cuts;
+    std::vector<int> order;
+    if (spec && spec->cuts.size() >= 2 && dm->coototal > 0)
     {
-        int dev = 0, l2 = 0;
-        TSP_CUDA(cudaGetDevice(&dev));
-        TSP_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
-        const long long budget = (long long)l2 / 2; // config-5 shard: 33 MB panels 1.32 ms, 50 MB 1.08, 67 MB 1.06, 100 MB 1.25
-        if ((long long)dm->colA * vs > 2 * budget)
-            panel_bytes = budget;
+        // explicit cuts (comm.cu: panels aligned with the row blocks of the ranks, launch order starting at the panel this
+        // rank owns): every range wider than panel_bytes (when > 0) is cut further into equal pieces
+        const long long maxc = panel_bytes > 0 ? std::max<long long>(TS, panel_bytes / vs / TS * TS) : 0;
+        int first = 0;
+        for (size_t k = 0; k + 1 < spec->cuts.size(); k++)
+        {
+            const long long a = spec->cuts[k], b = spec->cuts[k + 1];
+            if (b <= a)
+                continue;
+            const long long pieces = maxc > 0 ? (b - a + maxc - 1) / maxc : 1;
+            if ((int)k == spec->first_range)
+                first = (int)cuts.size();
+            for (long long q = 0; q < pieces; q++)
+                cuts.push_back(a + (b - a) * q / pieces);
+        }
+        cuts.push_back(std::max<long long>(spec->cuts.back(), dm->colA));
+        cuts[0] = 0;
+        const int np = (int)cuts.size() - 1;
+        if (np > 256)
+        {
+            set_error("plan: %d x panels (limit 256)", np);
+            return TILESPMV_ERR_INVALID;
+        }
+        for (int i = 0; i < np; i++)
+            order.push_back((first + i) % np);
     }
-    int npanels = 1;
-    long long panel_cols = 0;
-    if (panel_bytes > 0 && dm->coototal > 0)
+    else if (panel_bytes > 0 && dm->coototal > 0)
     {
-        panel_cols = std::max<long long>(TS, panel_bytes / vs / TS * TS);
+        long long panel_cols = std::max<long long>(TS, panel_bytes / vs / TS * TS);
         long long np = ((long long)dm->colA + panel_cols - 1) / panel_cols;
         if (np > 64) // bound the number of launches / y passes
         {
@@ -1338,14 +1447,17 @@ int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tiles
             panel_cols = (((long long)dm->colA + np - 1) / np + TS - 1) / TS * TS;
             np = ((long long)dm->colA + panel_cols - 1) / panel_cols;
         }
-        npanels = (int)std::max<long long>(np, 1);
+        for (long long p = 0; p <= np; p++)
+            cuts.push_back(p * panel_cols);
+        for (int p = 0; p < (int)np; p++)
+            order.push_back(p);
     }
-    if (npanels > 1)
+    if (order.size() > 1)
     {
         if (vs == 8)
-            TSP_TRY(plan_build_panels<double>(dm, P, npanels, panel_cols, s));
+            TSP_TRY(plan_build_panels<double>(dm, P, cuts, order, s));
         else
-            TSP_TRY(plan_build_panels<float>(dm, P, npanels, panel_cols, s));
+            TSP_TRY(plan_build_panels<float>(dm, P, cuts, order, s));
     }
     else
     {
@@ -1354,6 +1466,7 @@ int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tiles
             TSP_TRY(plan_build_t<double>(dm, src, P, s));
         else
             TSP_TRY(plan_build_t<float>(dm, src, P, s));
+        TSP_TRY(plan_col_range(dm, true, dm->deferredcoo_colidx.as<int>(), dm->coototal, P, s));
     }
 
     // roofline accounting, SURVEY.md 8(d): every quantity from the (bit-exact) Tile_matrix

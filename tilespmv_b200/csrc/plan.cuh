@@ -49,6 +49,9 @@ struct tilespmv_plan
     bool keep_all_rows = true; // emit an item for every block row, also empty ones
     std::vector<tilespmv_plan *> sub;
 
+    // the part of x this (sub-)plan's launch reads: columns [xcol_lo, xcol_hi)
+    long long xcol_lo = 0, xcol_hi = 0;
+
     // roofline accounting
     int64_t b_alg = 0, b_csr = 0;
 
@@ -65,6 +68,28 @@ struct tilespmv_plan
     tsp::DevBuf bx[HOST_RING], by[HOST_RING];
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[HOST_RING] = {nullptr}, ev_comp[HOST_RING] = {nullptr}, ev_out[HOST_RING] = {nullptr};
+    bool ring_ready = false; // set only once every stream, event and buffer of the ring exists
+    void release_host_ring()
+    {
+        for (int i = 0; i < HOST_RING; i++)
+        {
+            for (cudaEvent_t *e : {&ev_in[i], &ev_comp[i], &ev_out[i]})
+                if (*e)
+                {
+                    cudaEventDestroy(*e);
+                    *e = nullptr;
+                }
+            bx[i].release();
+            by[i].release();
+        }
+        for (cudaStream_t *st : {&s_in, &s_comp, &s_out})
+            if (*st)
+            {
+                cudaStreamDestroy(*st);
+                *st = nullptr;
+            }
+        ring_ready = false;
+    }
     // tilespmv_plan_iterate: the niters ping-pong launches captured once into a CUDA graph, re-instantiated only
     // when the buffers or the count change
     cudaStream_t s_capture = nullptr;
@@ -79,13 +104,7 @@ struct tilespmv_plan
             cudaStreamDestroy(s_capture);
         for (tilespmv_plan *q : sub)
             delete q;
-        for (int i = 0; i < HOST_RING; i++)
-            for (cudaEvent_t e : {ev_in[i], ev_comp[i], ev_out[i]})
-                if (e)
-                    cudaEventDestroy(e);
-        for (cudaStream_t st : {s_in, s_comp, s_out})
-            if (st)
-                cudaStreamDestroy(st);
+        release_host_ring();
     }
 
     int64_t device_bytes() const
@@ -100,7 +119,18 @@ struct tilespmv_plan
 
 namespace tsp
 {
-int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tilespmv_plan *plan, cudaStream_t s);
+// explicit column panels of the side matrix: ranges [cuts[k], cuts[k+1]); the launch order starts at range first_range
+struct PanelSpec
+{
+    std::vector<long long> cuts;
+    int first_range = 0;
+};
+int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tilespmv_plan *plan, cudaStream_t s,
+               const PanelSpec *spec = nullptr);
+int plan_panel_bytes(const tilespmv_dmat *dm, int xpanel_bytes, long long *out);
 int plan_launch(tilespmv_plan *plan, const void *d_x, void *d_y, cudaStream_t s);
+// one launch unit of a plan: unit 0 = the plan itself (writes y), unit i = column-panel sub-plan i-1 (accumulates);
+// fused peer stores ride on the unit flagged `with_peers`
+int plan_launch_unit(tilespmv_plan *plan, int unit, const void *d_x, void *d_y, cudaStream_t s, bool with_peers);
 int spmv_configure(tilespmv_plan *plan); // picks grid / smem, sets the kernel attributes
 } // namespace tsp

@@ -1041,4 +1041,18 @@ int plan_launch(tilespmv_plan *P, const void *d_x, void *d_y, cudaStream_t s)
     return plan_launch_t<float>(P, static_cast<const float *>(d_x), static_cast<float *>(d_y), s);
 }
 
+int plan_launch_unit(tilespmv_plan *P, int unit, const void *d_x, void *d_y, cudaStream_t s, bool with_peers)
+{
+    if (unit < 0 || unit > (int)P->sub.size() || (reinterpret_cast<uintptr_t>(d_x) & 15u) || (reinterpret_cast<uintptr_t>(d_y) & 15u))
+    {
+        set_error("spmv: bad launch unit or unaligned x / y");
+        return TILESPMV_ERR_INVALID;
+    }
+    tilespmv_plan *Q = unit == 0 ? P : P->sub[(size_t)unit - 1];
+    const int np = with_peers ? P->npeers : 0;
+    if (P->precision == 8)
+        return plan_launch_one<double>(Q, static_cast<const double *>(d_x), static_cast<double *>(d_y), s, np, P->peers, P->row_offset);
+    return plan_launch_one<float>(Q, static_cast<const float *>(d_x), static_cast<float *>(d_y), s, np, P->peers, P->row_offset);
+}
+
 } // namespace tsp

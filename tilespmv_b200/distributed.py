@@ -1,91 +1,108 @@
-"""One-process-per-GPU driver of the row-block sharded SpMV.
+"""Thin ctypes caller of the library's multi-GPU entry points (include/tilespmv.h: tilespmv_comm_* / tilespmv_dist_*).
 
-Every rank holds a self-contained Tile_matrix + plan for its contiguous range of block rows
-(tilespmv_b200/sharding.py picks the cuts) and a replicated x.  A single SpMV is communication
-free.  For the repeated-SpMV loop x <- A*x two exchanges are offered:
+One process per GPU.  Every rank converts its contiguous range of block rows (tilespmv_b200/sharding.py or
+tilespmv_partition_rows pick the cuts), the library owns everything else: the rendezvous (POSIX shared memory), the
+CUDA-IPC-mapped x buffers, the NCCL communicator and the three exchanges of the repeated-SpMV loop x <- A*x
 
-  "nccl"   baseline: the y slices (unequal lengths) are all-gathered into the next x with one
-           NCCL broadcast per rank in a coalesced group;
-  "fused"  the SpMV kernel's own epilogue stores every y value into the next-x buffer of every peer
-           through NVLink-mapped pointers (torch symmetric memory = CUDA VMM peer mappings handed to
-           tilespmv_plan_set_peers), so the all-gather IS the kernel's store stream and overlaps the
-           HBM-bound compute; one device-side barrier per iteration orders the double-buffered x.
+  "nccl"       SpMV, then ncclAllGather / grouped ncclBroadcast            (baseline)
+  "fused"      the kernel's epilogue stores y into every peer's next x      (NVLink P2P stores)
+  "pipelined"  copy-engine pushes ordered by need + per-launch waits        (exchange hidden under the next iteration)
 
-PyTorch is plumbing here (device memory, streams, process groups); the arithmetic is the C-ABI library.
+Nothing here needs torch: device pointers are plain ints.  torch shows up only in callers that want tensors.
 """
-import numpy as np
-import torch
-import torch.distributed as dist
+import ctypes as C
+import os
 
-from . import api, sharding
+import numpy as np
+
+from . import _capi, api, sharding
+
+EXCHANGES = {"nccl": _capi.EXCHANGE_NCCL, "fused": _capi.EXCHANGE_FUSED, "pipelined": _capi.EXCHANGE_PIPELINED}
+
+
+class Comm:
+    """tilespmv_comm: rendezvous of `nranks` processes of one box under a job-unique `name`."""
+
+    def __init__(self, name, rank, nranks, nccl=True):
+        L = _capi.load()
+        h = C.c_void_p()
+        _capi.check(L.tilespmv_comm_create(name.encode(), rank, nranks, _capi.COMM_NCCL if nccl else 0, C.byref(h)),
+                    "tilespmv_comm_create")
+        self.handle, self.rank, self.nranks, self.has_nccl = h, rank, nranks, nccl
+
+    def barrier(self):
+        _capi.check(_capi.load().tilespmv_comm_barrier(self.handle), "tilespmv_comm_barrier")
+
+    def destroy(self):
+        if self.handle:
+            _capi.load().tilespmv_comm_destroy(self.handle)
+            self.handle = None
+
+
+def job_name(default="job"):
+    """A rendezvous name all ranks of a torchrun / mp.spawn job agree on and no other job shares."""
+    return f"{default}_{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', os.getppid())}"
 
 
 class ShardedSpMV:
-    def __init__(self, rows, rank, colA, local_rowptr, local_colidx, local_val, plan_kwargs=None, group=None):
-        """rows: list of (r0, r1) per rank (sharding.row_ranges); local_*: CSR of rows[rank]."""
-        self.rows, self.rank, self.colA, self.group = rows, rank, colA, group
-        self.r0, self.r1 = rows[rank]
+    """tilespmv_dist: this rank's row block of a square matrix + the replicated x."""
+
+    def __init__(self, comm, rows, colA, local_rowptr, local_colidx, local_val, plan_kwargs=None, uniform_panels=False):
+        """rows: list of (r0, r1) per rank (sharding.row_ranges); local_*: CSR of rows[comm.rank], global columns."""
+        L = _capi.load()
+        self.comm, self.rows, self.rank, self.colA = comm, rows, comm.rank, colA
+        self.r0, self.r1 = rows[comm.rank]
         self.m_local = self.r1 - self.r0
         self.dm = api.DeviceTileMatrix.from_csr(self.m_local, colA, local_rowptr, local_colidx, local_val)
-        self.plan = api.Plan(self.dm, **(plan_kwargs or {}))
-        self.dtype = torch.float64 if self.dm.precision == api.F64 else torch.float32
-        self._symm = None
+        self.val_dtype = self.dm.val_dtype
+        kw = dict(plan_kwargs or {})
+        opts = _capi.PlanOptions(kw.get("chunk_bytes", 0), kw.get("xstage_bytes", 0), kw.get("ctas_per_sm", 0), kw.get("stages", 0),
+                                 kw.get("max_warps", 0), 0 if kw.get("csr_groups", True) else _capi.PLAN_NO_CSR_GROUPS,
+                                 kw.get("xpanel_bytes", 0))
+        cuts = (C.c_int64 * (comm.nranks + 1))(*([r[0] for r in rows] + [rows[-1][1]]))
+        h = C.c_void_p()
+        _capi.check(L.tilespmv_dist_create(comm.handle, self.dm.handle, cuts, C.byref(opts),
+                                           _capi.DIST_UNIFORM_PANELS if uniform_panels else 0, C.byref(h)), "tilespmv_dist_create")
+        self.handle = h
+        # the rank's plan, borrowed from the dist object (never destroyed from here)
+        self.plan = api.Plan.__new__(api.Plan)
+        self.plan.handle = C.c_void_p(L.tilespmv_dist_plan(h))
+        self.plan.precision, self.plan.rowA, self.plan.colA, self.plan.val_dtype = self.dm.precision, self.m_local, colA, self.val_dtype
+        self.plan.destroy = lambda: None
 
-    # ---- single SpMV: y_local = A[r0:r1, :] @ x, no communication ----
-    def spmv(self, x, y_local, stream=None):
-        s = (stream or torch.cuda.current_stream()).cuda_stream
-        self.plan.spmv(x.data_ptr(), y_local.data_ptr(), s)
+    def info(self):
+        i = _capi.DistInfo()
+        _capi.check(_capi.load().tilespmv_dist_get_info(self.handle, C.byref(i)), "tilespmv_dist_get_info")
+        return i
+
+    # ---- single SpMV: y_local = A[r0:r1, :] @ x, no communication (raw device pointers) ----
+    def spmv(self, d_x, d_y_local, stream=0):
+        self.plan.spmv(d_x, d_y_local, stream)
 
     # ---- repeated SpMV ----
-    def _ensure_symmetric(self, n):
-        if self._symm is None:
-            import torch.distributed._symmetric_memory as symm_mem
-            g = self.group or dist.group.WORLD
-            bufs = [symm_mem.empty(n, dtype=self.dtype, device="cuda") for _ in range(2)]
-            hdls = [symm_mem.rendezvous(b, g) for b in bufs]
-            self._symm = (bufs, hdls)
-        return self._symm
+    def iterate(self, d_x0, iters, mode="pipelined", stream=0):
+        """x_{k+1} = A @ x_k for `iters` steps, asynchronous on `stream`; d_x0 = device pointer of the replicated start
+        vector (or 0 / None to continue).  Returns the device pointer of the replicated result (library-owned)."""
+        L = _capi.load()
+        _capi.check(L.tilespmv_dist_iterate(self.handle, C.c_void_p(d_x0 or None), iters, EXCHANGES[mode], C.c_void_p(stream)),
+                    "tilespmv_dist_iterate")
+        return L.tilespmv_dist_x(self.handle)
 
-    def iterate(self, x0, iters, mode="nccl", scale=1.0):
-        """x_{k+1} = A @ x_k for `iters` steps (square A); returns the final replicated x.
-        `scale` is unused by the kernels (plain x <- A*x like SURVEY.md 8d config 5)."""
-        n = self.colA
-        world = dist.get_world_size(self.group)
-        stream = torch.cuda.current_stream().cuda_stream
-        if mode == "nccl":
-            xs = [x0.clone(), torch.empty_like(x0)]
-            y = torch.empty(max(self.m_local, 1), dtype=self.dtype, device="cuda")
-            for i in range(iters):
-                src, dst = xs[i & 1], xs[(i + 1) & 1]
-                self.plan.spmv(src.data_ptr(), y.data_ptr(), stream)
-                sharding.allgather_rows(dist, y, self.rows, dst, self.group)
-            self.plan.set_peers([], 0)
-            return xs[iters & 1]
-        if mode != "fused":
-            raise ValueError(mode)
-        bufs, hdls = self._ensure_symmetric(n)
-        bufs[0].copy_(x0)
-        hdls[0].barrier(channel=0)
-        esz = bufs[0].element_size()
-        for i in range(iters):
-            src, dst = i & 1, (i + 1) & 1
-            peers = [int(hdls[dst].buffer_ptrs[r]) for r in range(world) if r != self.rank]
-            self.plan.set_peers(peers, self.r0)
-            # the local slice of the next x is this rank's y: the kernel writes it in place
-            self.plan.spmv(bufs[src].data_ptr(), bufs[dst].data_ptr() + self.r0 * esz, stream)
-            hdls[dst].barrier(channel=0)  # everybody's stores into everybody's next x are done
-        self.plan.set_peers([], 0)
-        return bufs[iters & 1]
+    def sync(self, stream=0):
+        _capi.check(_capi.load().tilespmv_dist_sync(self.handle, C.c_void_p(stream)), "tilespmv_dist_sync")
+
+    def destroy(self):
+        if self.handle:
+            _capi.load().tilespmv_dist_destroy(self.handle)
+            self.handle = None
+            self.plan.handle = None
+            self.dm.destroy()
 
 
-def build_sharded(rowA, colA, rowptr, colidx, val, plan_kwargs=None, group=None):
-    """Convenience for matrices that fit on the host of every rank: partition by streamed bytes and
-    build this rank's shard."""
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+def build_sharded(comm, rowA, colA, rowptr, colidx, val, plan_kwargs=None, uniform_panels=False):
+    """Convenience for matrices that fit on the host of every rank: partition by streamed bytes and build this rank's shard."""
     vs = 8 if np.asarray(val).dtype == np.float64 else 4
-    w = sharding.block_row_weights(rowptr, rowA, vs)
-    parts = sharding.partition(w, world)
-    rows = sharding.row_ranges(parts, rowA)
-    r0, r1 = rows[rank]
+    rows = sharding.partition_rows(rowptr, rowA, comm.nranks, vs)
+    r0, r1 = rows[comm.rank]
     lrp, lci, lv = sharding.shard_csr(rowptr, colidx, val, r0, r1)
-    return ShardedSpMV(rows, rank, colA, lrp, lci, lv, plan_kwargs, group)
+    return ShardedSpMV(comm, rows, colA, lrp, lci, lv, plan_kwargs, uniform_panels)
