@@ -244,6 +244,65 @@ int64_t tsgen_banded(int64_t N, int hb, int per_row, uint64_t seed, int val_mode
     return rowptr[N];
 }
 
+/* rows [row0, row0 + nrows) of the SAME banded matrix (local rowptr, global columns, identical values): a shard
+ * generates only its own row block.  Rows hb <= i < N - hb are never clipped and hold take + 1 entries, so the global
+ * position of the first entry needs only the two clipped edge zones. */
+int64_t tsgen_banded_rows(int64_t N, int64_t row0, int64_t nrows, int hb, int per_row, uint64_t seed, int val_mode,
+                          int *rowptr, int *colidx, double *val)
+{
+    if (hb > 255) hb = 255;
+    if (row0 < 0 || nrows < 0 || row0 + nrows > N)
+        return -1;
+    const int take = per_row < 2 * hb ? per_row : 2 * hb;
+    int64_t base = 0; /* entries of rows [0, row0) */
+    for (int64_t i = 0; i < row0;)
+    {
+        if (i >= hb && i < N - hb)
+        {
+            const int64_t stop = row0 < N - hb ? row0 : N - hb;
+            base += (stop - i) * (int64_t)(take + 1);
+            i = stop;
+            continue;
+        }
+        int cols[520];
+        base += banded_row(N, i, hb, per_row, seed, cols);
+        i++;
+    }
+    if (!rowptr)
+    {
+        int64_t nnz = 0;
+#pragma omp parallel for schedule(static, 4096) reduction(+ : nnz)
+        for (int64_t r = 0; r < nrows; r++)
+        {
+            int cols[520];
+            nnz += banded_row(N, row0 + r, hb, per_row, seed, cols);
+        }
+        return nnz;
+    }
+#pragma omp parallel for schedule(static, 4096)
+    for (int64_t r = 0; r < nrows; r++)
+    {
+        int cols[520];
+        rowptr[r] = banded_row(N, row0 + r, hb, per_row, seed, cols);
+    }
+    rowptr[nrows] = 0;
+    prefix_from_counts(nrows, rowptr);
+#pragma omp parallel for schedule(static, 4096)
+    for (int64_t r = 0; r < nrows; r++)
+    {
+        int cols[520];
+        const int64_t i = row0 + r;
+        int n = banded_row(N, i, hb, per_row, seed, cols);
+        for (int k = 0; k < n; k++)
+        {
+            const int64_t p = rowptr[r] + k, pg = base + p; /* local / global position */
+            colidx[p] = (int)(i + cols[k]);
+            val[p] = val_mode == 1 ? (double)(pg % 10) : u11(rnd3(seed ^ 0x5151ull, (uint64_t)i, (uint64_t)pg));
+        }
+    }
+    return rowptr[nrows];
+}
+
 /* ---- contiguous band |i-j| <= hb (config 3b: Dense + CSR + COO tile mix) ---- */
 int64_t tsgen_band_contig(int64_t N, int hb, uint64_t seed, int val_mode, int *rowptr, int *colidx,
                           double *val)

@@ -18,7 +18,7 @@ def _L():
     if _lib is None:
         _lib = C.CDLL(build.build_gen())
         for name in ("tsgen_lap2d", "tsgen_lap3d27", "tsgen_banded", "tsgen_band_contig",
-                     "tsgen_uniform_rows", "tsgen_rmat", "tsgen_seven_formats", "tsgen_lap3d27_slab"):
+                     "tsgen_uniform_rows", "tsgen_banded_rows", "tsgen_rmat", "tsgen_seven_formats", "tsgen_lap3d27_slab"):
             getattr(_lib, name).restype = C.c_int64
     return _lib
 
@@ -76,6 +76,18 @@ def banded(N, hb=64, per_row=36, seed=3, val_mode=0):
     rp, ci, v = _alloc(N, nnz)
     f(*a, *_ptrs(rp, ci, v))
     return N, N, rp, ci, v
+
+
+def banded_rows(N, row0, nrows, hb=64, per_row=36, seed=3, val_mode=0):
+    """Rows [row0, row0+nrows) of banded(N, ...): local rowptr, global columns, the same values as the full matrix."""
+    f = _L().tsgen_banded_rows
+    a = (C.c_int64(N), C.c_int64(row0), C.c_int64(nrows), C.c_int(hb), C.c_int(per_row), C.c_uint64(seed), C.c_int(val_mode))
+    nnz = f(*a, *_NULLS)
+    if nnz < 0:
+        raise ValueError("row range outside the matrix")
+    rp, ci, v = _alloc(nrows, nnz)
+    f(*a, *_ptrs(rp, ci, v))
+    return nrows, N, rp, ci, v
 
 
 def band_contig(N, hb=18, seed=3, val_mode=0):
