@@ -244,7 +244,10 @@ typedef struct
                          (panels only when x is far larger than L2 and side entries dominate),
                          > 0 = that width, < 0 = never.  With panels one SpMV is one launch per
                          panel, each gathering from an L2-resident window of x.                */
-    int reserved[1];
+    int format_mask;  /* per-format cost profiling (cf. DEBUG_FORMATCOST / formatprofile, tilespmv_cuda.h:102-111,
+                         main.cu:12): 0 = the whole matrix; else bit f (TILESPMV_FMT_*) keeps the tiles of format f, bit 1
+                         (COO) the extracted side entries (COO tiles + HYB spill-over).  The plans of the seven single
+                         bits partition the nonzeros: their y's add up to A*x. */
 } tilespmv_plan_options;
 /* keep every CSR tile an individual tile of the packed stream instead of merging the CSR tiles of a block row
  * into one jagged slot-row list (the default, faster; results agree to rounding) */
@@ -366,6 +369,18 @@ typedef struct
     int64_t xpanels;           /* column panels of the side matrix (1 = none; see xpanel_bytes) */
 } tilespmv_plan_info;
 int tilespmv_plan_get_info(const tilespmv_plan *plan, tilespmv_plan_info *info);
+
+/*
+ * Per-format cost profile (the reference's DEBUG_FORMATCOST build, tilespmv_cuda.h:102-111: its kernel restricted to one
+ * format, formatprofile = -1 all / 0..6 / 7 none).  Builds one plan per format present in dm (+ the whole matrix + an
+ * empty plan that only writes zeros) and times `iters` SpMVs of each on the device vectors d_x / d_y:
+ *   ms[f], f = 0..6   the tiles of format f only (f = 1: the extracted side entries); 0 when the format is absent
+ *   ms[7]             no format at all: the fixed cost of visiting every block row and writing y
+ *   ms[8]             the whole matrix
+ * nnz[f] (may be NULL) receives the nonzeros each of those plans multiplies (nnz[7] = 0, nnz[8] = all).
+ */
+int tilespmv_format_profile(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, const void *d_x, void *d_y, int warmup,
+                            int iters, double ms[9], int64_t nnz[9]);
 
 /* Time `iters` back-to-back SpMVs on device buffers with CUDA events on `stream` (after
  * `warmup` untimed ones); returns mean milliseconds per SpMV in *ms_per_spmv. */

@@ -346,3 +346,35 @@ def test_random_matrices_all_plan_variants(seed):
                 dict(chunk_bytes=2560, xstage_bytes=256, xpanel_bytes=512, csr_groups=False)]
     check_matrix(case, precision, plan_kwargs=variants[seed % len(variants)], enable_hyb=seed % 4 == 0)
     check_matrix(case, precision, plan_kwargs=variants[(seed + 1) % len(variants)])
+
+
+# ---- per-format cost profiling (cf. DEBUG_FORMATCOST / formatprofile, tilespmv_cuda.h:102-111, main.cu:12) ----
+@pytest.mark.parametrize("name", ["seven_formats", "band_contig_8k", "rmat_12", "lap3d27_24", "ragged_seven", "hyb_rich"])
+def test_single_format_plans_partition_the_matrix(name):
+    """A plan restricted to one tile format multiplies exactly the nonzeros of that format (bit 1 = the extracted side
+    entries): on the reference driver's integer data the seven partial y's add up to y bit for bit, the empty mask gives
+    zeros, and tilespmv_format_profile reports a time for every format that is present."""
+    import torch
+    from tests.cases import HYB_CASES
+    hyb = name == "hyb_rich"
+    m, n, rp, ci, v = (HYB_CASES if hyb else CASES)[name]()
+    v = (np.arange(len(ci)) % 10).astype(np.float64)
+    x = x_for(n, 1)
+    dm = api.DeviceTileMatrix.from_csr(m, n, rp, ci, v, enable_hyb=hyb)
+    info = dm.info()
+    y_all = api.Plan(dm).spmv_host(x)
+    total = np.zeros(m)
+    for f in range(7):
+        y_f = api.Plan(dm, format_mask=1 << f).spmv_host(x)
+        present = info.tiles_by_format[f] > 0 or (f == 1 and info.nnz_side > 0)
+        assert present or not y_f.any(), f"format {f} is absent but its plan produced values"
+        total += y_f
+    assert total.tobytes() == y_all.tobytes()
+    assert not api.Plan(dm, format_mask=0x80).spmv_host(x).any()
+    d_x, d_y = torch.from_numpy(x).cuda(), torch.empty(max(m, 1), dtype=torch.float64, device="cuda")
+    ms, nnz = api.format_profile(dm, d_x.data_ptr(), d_y.data_ptr(), warmup=1, iters=3)
+    assert nnz[8] == int(rp[m]) and sum(nnz[:7]) == nnz[8] and nnz[1] == info.nnz_side
+    for f in range(7):
+        present = info.tiles_by_format[f] > 0 or (f == 1 and info.nnz_side > 0)
+        assert (ms[f] > 0) == present and (nnz[f] > 0) == present
+    assert ms[7] > 0 and ms[8] > 0

@@ -63,7 +63,7 @@ class DmatInfo(C.Structure):
 
 class PlanOptions(C.Structure):
     _fields_ = [("chunk_bytes", C.c_int), ("xstage_bytes", C.c_int), ("ctas_per_sm", C.c_int),
-                ("stages", C.c_int), ("max_warps", C.c_int), ("flags", C.c_int), ("xpanel_bytes", C.c_int), ("reserved", C.c_int * 1)]
+                ("stages", C.c_int), ("max_warps", C.c_int), ("flags", C.c_int), ("xpanel_bytes", C.c_int), ("format_mask", C.c_int)]
 
 
 class DistInfo(C.Structure):
@@ -92,7 +92,7 @@ EXPORTS = [
     "tilespmv_convert", "tilespmv_dmat_upload_f64", "tilespmv_dmat_upload_f32",
     "tilespmv_dmat_export_f64", "tilespmv_dmat_export_f32", "tilespmv_dmat_destroy",
     "tilespmv_dmat_get_info", "tilespmv_plan_create", "tilespmv_plan_destroy", "tilespmv_plan_spmv",
-    "tilespmv_plan_spmv_host", "tilespmv_plan_spmv_host_batch", "tilespmv_plan_iterate", "tilespmv_partition_rows", "tilespmv_plan_set_peers", "tilespmv_plan_get_info", "tilespmv_plan_time",
+    "tilespmv_plan_spmv_host", "tilespmv_plan_spmv_host_batch", "tilespmv_plan_iterate", "tilespmv_partition_rows", "tilespmv_plan_set_peers", "tilespmv_plan_get_info", "tilespmv_plan_time", "tilespmv_format_profile",
     "tilespmv_mmio_allinone_f64", "tilespmv_mmio_allinone_f32", "tilespmv_last_error",
     "tilespmv_version", "tilespmv_kernel_launch_count",
     "tilespmv_comm_create", "tilespmv_comm_destroy", "tilespmv_comm_barrier", "tilespmv_dist_create",
@@ -134,6 +134,8 @@ def load(rebuild=False):
     L.tilespmv_plan_iterate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.tilespmv_plan_time.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                      C.POINTER(C.c_double)]
+    L.tilespmv_format_profile.argtypes = [C.c_void_p, C.POINTER(PlanOptions), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                          C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.tilespmv_plan_set_peers.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int64]
     L.tilespmv_plan_create.argtypes = [C.c_void_p, C.POINTER(PlanOptions), C.POINTER(C.c_void_p)]
     L.tilespmv_plan_destroy.argtypes = [C.c_void_p]

@@ -176,10 +176,10 @@ class Plan:
     """tilespmv_plan: packed stream + persistent chunk schedule for one DeviceTileMatrix."""
 
     def __init__(self, dmat, chunk_bytes=0, xstage_bytes=0, ctas_per_sm=0, stages=0, max_warps=0, csr_groups=True,
-                 xpanel_bytes=0):
+                 xpanel_bytes=0, format_mask=0):
         L = _capi.load()
         opts = _capi.PlanOptions(chunk_bytes, xstage_bytes, ctas_per_sm, stages, max_warps,
-                                 0 if csr_groups else _capi.PLAN_NO_CSR_GROUPS, xpanel_bytes)
+                                 0 if csr_groups else _capi.PLAN_NO_CSR_GROUPS, xpanel_bytes, format_mask)
         h = C.c_void_p()
         check(L.tilespmv_plan_create(dmat.handle, C.byref(opts), C.byref(h)), "tilespmv_plan_create")
         self.handle, self.precision = h, dmat.precision
@@ -240,6 +240,16 @@ class Plan:
             self.destroy()
         except Exception:
             pass
+
+
+def format_profile(dmat, d_x, d_y, warmup=3, iters=20):
+    """tilespmv_format_profile: ms per SpMV restricted to each tile format (0..6), to no format (7) and for the whole
+    matrix (8), and the nonzeros each of those plans multiplies."""
+    ms = (C.c_double * 9)()
+    nnz = (C.c_int64 * 9)()
+    check(_capi.load().tilespmv_format_profile(dmat.handle, None, C.c_void_p(d_x), C.c_void_p(d_y), warmup, iters, ms, nnz),
+          "tilespmv_format_profile")
+    return list(ms), list(nnz)
 
 
 def mmio_allinone(filename, precision=F64):

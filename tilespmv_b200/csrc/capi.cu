@@ -493,6 +493,69 @@ static int plan_time_impl(tilespmv_plan *P, const void *d_x, void *d_y, int warm
     return TILESPMV_OK;
 }
 
+__global__ void __launch_bounds__(256)
+    nnz_by_format_kernel(int T, const char *__restrict__ fmt, const int *__restrict__ tile_nnz, unsigned long long *__restrict__ out)
+{
+    __shared__ unsigned long long acc[7];
+    if (threadIdx.x < 7)
+        acc[threadIdx.x] = 0;
+    __syncthreads();
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x)
+    {
+        const int f = fmt[t];
+        if (f >= 0 && f < 7)
+            atomicAdd(&acc[f], (unsigned long long)(tile_nnz[t + 1] - tile_nnz[t]));
+    }
+    __syncthreads();
+    if (threadIdx.x < 7 && acc[threadIdx.x])
+        atomicAdd(&out[threadIdx.x], acc[threadIdx.x]);
+}
+
+static int format_profile_impl(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, const void *d_x, void *d_y, int warmup,
+                               int iters, double ms[9], int64_t nnz[9])
+{
+    DevBuf d_n;
+    TSP_TRY(d_n.alloc(7 * sizeof(unsigned long long), true));
+    if (dm->tilenum > 0)
+        TSP_LAUNCH(nnz_by_format_kernel, std::min(grid_for((size_t)dm->tilenum, 256), 1024u), 256, 0, 0, dm->tilenum, dm->Format.as<char>(),
+                   dm->tile_nnz.as<int>(), d_n.as<unsigned long long>());
+    unsigned long long h[7];
+    TSP_CUDA(cudaMemcpy(h, d_n.p, sizeof(h), cudaMemcpyDeviceToHost));
+    // the extracted side entries are the COO tiles' nonzeros plus what HYB tiles spill (csr2tile.h:316, :538-545)
+    const long long spill = (long long)dm->coototal - (long long)h[TILESPMV_FMT_COO];
+    if (nnz)
+    {
+        for (int f = 0; f < 7; f++)
+            nnz[f] = (int64_t)h[f];
+        nnz[TILESPMV_FMT_COO] = dm->coototal;
+        nnz[TILESPMV_FMT_HYB] -= spill;
+        nnz[7] = 0;
+        nnz[8] = dm->nnz;
+    }
+    for (int k = 0; k < 9; k++)
+    {
+        ms[k] = 0.0;
+        const bool present = k >= 7 || dm->fmt_hist[k] > 0 || (k == TILESPMV_FMT_COO && dm->coototal > 0);
+        if (!present)
+            continue;
+        tilespmv_plan_options o;
+        memset(&o, 0, sizeof(o));
+        if (opts)
+            o = *opts;
+        // k = 7: a mask with no format bit (bit 7 only keeps it non-zero, i.e. "restricted"); k = 8: everything
+        o.format_mask = k < 7 ? (1 << k) : (k == 7 ? 0x80 : 0);
+        tilespmv_plan *P = new (std::nothrow) tilespmv_plan();
+        if (!P)
+            return TILESPMV_ERR_ALLOC;
+        int rc = plan_build(dm, &o, P, 0);
+        if (rc == TILESPMV_OK)
+            rc = plan_time_impl(P, d_x, d_y, warmup, iters, 0, &ms[k]);
+        delete P;
+        TSP_TRY(rc);
+    }
+    return TILESPMV_OK;
+}
+
 static int env_int(const char *name, int dflt)
 {
     const char *v = getenv(name);
@@ -548,7 +611,22 @@ static void call_entry(char *filename, TM *matrix, int rowA, int colA, int nnzA,
     printf("  CUDA SpMV runtime %4.2f ms, %4.2f GFlops\n\n", ms, gflops);
     if (FILE *f = fopen("results.csv", "a"))
     {
-        fprintf(f, "%s,%i,%i,%i,%f,%f\n", filename ? filename : "", rowA, colA, nnzA, ms, gflops);
+        // the reference's six columns (tilespmv_cuda.h:1142-1147) stay the default so that existing sweep scripts keep
+        // parsing the file; TILESPMV_CSV_EXTENDED=1 appends the roofline columns SURVEY.md 8f-4 asks for:
+        // algorithmic bytes (8d), achieved GB/s on them, fraction of the HBM peak (TILESPMV_HBM_PEAK_GBS, default the
+        // nominal 8000 GB/s of BASELINE.json)
+        if (env_int("TILESPMV_CSV_EXTENDED", 0))
+        {
+            double peak = 8000.0;
+            if (const char *e = getenv("TILESPMV_HBM_PEAK_GBS"))
+                if (atof(e) > 0)
+                    peak = atof(e);
+            const double gbps = ms > 0 ? (double)P->b_alg * 1e-6 / ms : 0.0;
+            fprintf(f, "%s,%i,%i,%i,%f,%f,%lld,%f,%f\n", filename ? filename : "", rowA, colA, nnzA, ms, gflops, (long long)P->b_alg, gbps,
+                    gbps / peak);
+        }
+        else
+            fprintf(f, "%s,%i,%i,%i,%f,%f\n", filename ? filename : "", rowA, colA, nnzA, ms, gflops);
         fclose(f);
     }
     if (rowA && cudaMemcpy(y, dy.p, (size_t)rowA * sizeof(T), cudaMemcpyDeviceToHost) != cudaSuccess)
@@ -1296,6 +1374,19 @@ int tilespmv_plan_get_info(const tilespmv_plan *plan, tilespmv_plan_info *info)
     info->device_bytes = plan->device_bytes();
     info->csr_groups = plan->csr_groups;
     return TILESPMV_OK;
+}
+
+int tilespmv_format_profile(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, const void *d_x, void *d_y, int warmup, int iters,
+                            double ms[9], int64_t nnz[9])
+{
+    clear_error();
+    if (!dm || !ms || (!d_x && dm->colA) || (!d_y && dm->rowA))
+    {
+        set_error("format_profile: null argument");
+        return TILESPMV_ERR_INVALID;
+    }
+    TSP_TRY(require_device());
+    return format_profile_impl(dm, opts, d_x, d_y, warmup, iters, ms, nnz);
 }
 
 int tilespmv_plan_time(tilespmv_plan *plan, const void *d_x, void *d_y, int warmup, int iters, void *stream,

@@ -91,6 +91,7 @@ struct tilespmv_dist
     size_t x_off[2] = {0, 0}, xbytes = 0;
     unsigned char *peer_block[tsp::COMM_MAX_RANKS] = {nullptr};
     bool peer_mapped[tsp::COMM_MAX_RANKS] = {false};
+    int peer_device[tsp::COMM_MAX_RANKS] = {0};
     cudaStream_t s_comm = nullptr;
     cudaEvent_t ev_kernel[2] = {nullptr, nullptr}, ev_push[2] = {nullptr, nullptr};
     bool ev_push_valid[2] = {false, false};
@@ -98,7 +99,11 @@ struct tilespmv_dist
     int cur = 0;        // x buffer holding the current x
     std::vector<uint32_t> deps; // per launch unit: bit mask of the source ranks whose slices it reads (self excluded)
     unsigned long long spin_timeout_ns = 30ull * 1000000000ull;
-    int64_t launches_per_iteration[3] = {0, 0, 0};
+    // TILESPMV_DIST_DEBUG=1: CUDA-event timing of the LAST push of every pipelined call, printed by tilespmv_dist_sync
+    bool debug = false, dbg_armed = false;
+    cudaEvent_t dbg0 = nullptr, dbg1 = nullptr;
+    size_t dbg_bytes = 0;
+    int dbg_dst = 0;
     ~tilespmv_dist()
     {
         for (int r = 0; r < tsp::COMM_MAX_RANKS; r++)
@@ -490,6 +495,7 @@ static int dist_create(tilespmv_comm *c, const tilespmv_dmat *dm, const int64_t 
         return fail(TILESPMV_ERR_CUDA);
     }
     d->peer_block[me] = d->block.as<unsigned char>();
+    d->peer_device[me] = c->device;
     if (R > 1)
     {
         ShmSlot &mine = c->seg->slot[me];
@@ -520,6 +526,22 @@ static int dist_create(tilespmv_comm *c, const tilespmv_dmat *dm, const int64_t 
                 set_error("dist_create: ranks %d and %d share a process; use one process per rank (CUDA IPC)", r, me);
                 return fail(TILESPMV_ERR_UNSUPPORTED);
             }
+            // peer access must be enabled explicitly for the COPY path: cudaIpcMemLazyEnablePeerAccess alone lets
+            // kernels store through the mapping, but cudaMemcpyAsync between the two devices then stages through the
+            // host (measured: 25-30 GB/s instead of NVLink speed)
+            if (o.device != c->device)
+            {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, c->device, o.device);
+                cudaError_t pe = can ? cudaDeviceEnablePeerAccess(o.device, 0) : cudaErrorPeerAccessUnsupported;
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
+                {
+                    cudaGetLastError();
+                    set_error("dist_create: no peer access from device %d to device %d (%s)", c->device, o.device, cudaGetErrorString(pe));
+                    return fail(TILESPMV_ERR_CUDA);
+                }
+                cudaGetLastError();
+            }
             void *p = nullptr;
             cudaError_t e = cudaIpcOpenMemHandle(&p, o.handle, cudaIpcMemLazyEnablePeerAccess);
             if (e != cudaSuccess)
@@ -530,10 +552,18 @@ static int dist_create(tilespmv_comm *c, const tilespmv_dmat *dm, const int64_t 
             }
             d->peer_block[r] = static_cast<unsigned char *>(p);
             d->peer_mapped[r] = true;
+            d->peer_device[r] = o.device;
         }
         rc = comm_barrier(c); // every rank has read every slot: the slots may be re-used by the next dist_create
         if (rc != TILESPMV_OK)
             return fail(rc);
+    }
+    if (const char *e = getenv("TILESPMV_DIST_DEBUG"))
+        d->debug = atoi(e) != 0;
+    if (d->debug)
+    {
+        cudaEventCreate(&d->dbg0);
+        cudaEventCreate(&d->dbg1);
     }
     if (cudaStreamCreateWithFlags(&d->s_comm, cudaStreamNonBlocking) != cudaSuccess)
     {
@@ -654,8 +684,19 @@ static int iterate_pipelined(tilespmv_dist *d, int niters, cudaStream_t s)
         {
             const int dst = (me - k + R) % R;
             TSP_TRY(flag_wait(d, DIST_OFF_A, 1u << dst, e, d->s_comm)); // dst finished epoch e - 1 (or entered the call)
+            const bool dbg = d->debug && i == niters - 1 && k == 1 && slice_bytes;
+            if (dbg)
+                TSP_CUDA(cudaEventRecord(d->dbg0, d->s_comm));
             if (slice_bytes)
-                TSP_CUDA(cudaMemcpyAsync(xbuf(d, dst, db) + slice_off, xbuf(d, me, db) + slice_off, slice_bytes, cudaMemcpyDeviceToDevice, d->s_comm));
+                TSP_CUDA(cudaMemcpyPeerAsync(xbuf(d, dst, db) + slice_off, d->peer_device[dst], xbuf(d, me, db) + slice_off, d->comm->device,
+                                             slice_bytes, d->s_comm));
+            if (dbg)
+            {
+                TSP_CUDA(cudaEventRecord(d->dbg1, d->s_comm));
+                d->dbg_armed = true;
+                d->dbg_bytes = slice_bytes;
+                d->dbg_dst = dst;
+            }
             TSP_TRY(flag_signal(d, DIST_OFF_D, 1u << dst, e + 1, d->s_comm));
         }
         TSP_CUDA(cudaEventRecord(d->ev_push[i & 1], d->s_comm));
@@ -765,6 +806,14 @@ int tilespmv_dist_sync(tilespmv_dist *dist, void *stream)
     }
     TSP_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     TSP_CUDA(cudaStreamSynchronize(dist->s_comm));
+    if (dist->dbg_armed)
+    {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, dist->dbg0, dist->dbg1) == cudaSuccess)
+            fprintf(stderr, "[tilespmv_dist rank %d] push of %zu bytes to rank %d: %.3f ms = %.1f GB/s\n", dist->rank, dist->dbg_bytes,
+                    dist->dbg_dst, ms, ms > 0 ? dist->dbg_bytes * 1e-6 / ms : 0.0);
+        dist->dbg_armed = false;
+    }
     uint32_t err = 0;
     TSP_CUDA(cudaMemcpy(&err, dist->block.as<unsigned char>() + DIST_OFF_ERR, sizeof(err), cudaMemcpyDeviceToHost));
     if (err)

@@ -76,6 +76,15 @@ struct TileCostIn
     }
 };
 
+// per-format cost profiling (cf. DEBUG_FORMATCOST / formatprofile, tilespmv_cuda.h:102-111, main.cu:12): a plan restricted
+// to some formats sees every other tile as a COO tile, i.e. as not part of the stream
+__global__ void __launch_bounds__(PL_THREADS) filter_format_kernel(int T, const char *__restrict__ fmt, unsigned mask, char *__restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T)
+        out[t] = ((mask >> (unsigned)fmt[t]) & 1u) ? fmt[t] : (char)TILESPMV_FMT_COO;
+}
+
 struct TileScans // all T+1 entries
 {
     const int *nc;        // stream tiles
@@ -682,6 +691,17 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
     uint32_t C = (uint32_t)P->chunk_bytes, X = (uint32_t)P->xstage_bytes; // 0 = chosen below from the row sizes
     ScanWorkspace ws;
 
+    // formats this plan covers (0 = all): excluded tiles are treated like COO tiles (skipped by the stream)
+    DevBuf d_fmt_eff;
+    const char *fmt_eff = dm->Format.as<char>();
+    const unsigned fmask = (unsigned)P->format_mask & 0x7fu;
+    if (P->format_mask != 0 && fmask != 0x7fu && T_ > 0) // mask 0x80: restricted to NO format (only the fixed per-row cost is left)
+    {
+        TSP_TRY(d_fmt_eff.alloc((size_t)T_, false));
+        TSP_LAUNCH(filter_format_kernel, grid_for((size_t)T_, PL_THREADS), PL_THREADS, 0, s, T_, dm->Format.as<char>(), fmask, d_fmt_eff.as<char>());
+        fmt_eff = d_fmt_eff.as<char>();
+    }
+
     // ---- 1. per-tile prefix sums ----
     DevBuf d_nc, d_oc, d_ws, d_ob, d_hi, d_oc2, d_ob2;
     TSP_TRY(d_oc2.alloc((size_t)(T_ + 1) * sizeof(int), true, s));
@@ -693,7 +713,7 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
     TSP_TRY(d_hi.alloc((size_t)(T_ + 1) * sizeof(int), true, s));
     if (T_)
     {
-        TileCostIn tc{dm->Format.as<char>(), dm->tile_nnz.as<int>(), dm->tilewidth.as<char>(),
+        TileCostIn tc{fmt_eff, dm->tile_nnz.as<int>(), dm->tilewidth.as<char>(),
                       dm->dnsrowptr.as<int>(), dm->dnscolptr.as<int>(), T_, vs, TC_STREAM_TILES};
         TSP_TRY(exclusive_scan(tc, (size_t)T_ + 1, d_nc.as<int>(), ws, s, nullptr));
         tc.kind = TC_OTHER_TILES;
@@ -742,7 +762,7 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
         TSP_TRY(d_row_cn.alloc((size_t)tilem * sizeof(int), true, s));
         TSP_TRY(d_row_cs.alloc((size_t)tilem * sizeof(int), true, s));
         TSP_LAUNCH(row_csr_summary_kernel, grid_for((size_t)tilem, PL_THREADS), PL_THREADS, 0, s, tilem, rowA,
-                   dm->tile_ptr.as<int>(), dm->Format.as<char>(), dm->tile_nnz.as<int>(), dm->csrptr_offset.as<int>(),
+                   dm->tile_ptr.as<int>(), fmt_eff, dm->tile_nnz.as<int>(), dm->csrptr_offset.as<int>(),
                    dm->Blockcsr_Ptr.as<unsigned char>(), d_row_nt.as<int>(), d_row_cc.as<int>(), d_row_cn.as<int>(),
                    d_row_cs.as<int>());
         row_cc.resize(tilem);
@@ -1119,7 +1139,7 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
         a.tilen = dm->tilen;
         a.tile_columnidx = dm->tile_columnidx.as<int>();
         a.tile_nnz = dm->tile_nnz.as<int>();
-        a.Format = dm->Format.as<char>();
+        a.Format = fmt_eff;
         a.tilewidth = dm->tilewidth.as<char>();
         a.csr_offset = dm->csr_offset.as<int>();
         a.csrptr_offset = dm->csrptr_offset.as<int>();
@@ -1396,6 +1416,8 @@ int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tiles
     P->max_warps = opts ? opts->max_warps : 0;
     P->flags = opts ? opts->flags : 0;
     P->xpanel_bytes = opts ? opts->xpanel_bytes : 0;
+    P->format_mask = opts ? opts->format_mask : 0;
+    const bool with_side = P->format_mask == 0 || ((P->format_mask >> TILESPMV_FMT_COO) & 1);
     if (const char *e = getenv("TILESPMV_GATHER_SMEM_KB")) // experiments
         P->gather_smem_cap = atoi(e) * 1024;
     if ((P->chunk_bytes != 0 && (P->chunk_bytes < 2560 || P->chunk_bytes > 32768 || (P->chunk_bytes & 127))) ||
@@ -1452,6 +1474,9 @@ int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tiles
         for (int p = 0; p < (int)np; p++)
             order.push_back(p);
     }
+    const bool restricted = P->format_mask != 0 && (P->format_mask & 0x7f) != 0x7f;
+    if (restricted) // per-format profiling plans are single launches
+        order.clear();
     if (order.size() > 1)
     {
         if (vs == 8)
@@ -1461,11 +1486,16 @@ int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tiles
     }
     else
     {
-        PlanSource src{true, dm->tile_ptr.as<int>(), dm->deferredcoo_ptr.as<int>(), dm->deferredcoo_colidx.as<int>(), dm->deferredcoo_val.p};
+        DevBuf no_side; // a plan without the COO bit leaves the extracted entries out
+        if (!with_side)
+            TSP_TRY(no_side.alloc(((size_t)dm->rowA + 1) * sizeof(int), true, s));
+        PlanSource src{true, dm->tile_ptr.as<int>(), with_side ? dm->deferredcoo_ptr.as<int>() : no_side.as<int>(),
+                       dm->deferredcoo_colidx.as<int>(), dm->deferredcoo_val.p};
         if (vs == 8)
             TSP_TRY(plan_build_t<double>(dm, src, P, s));
         else
             TSP_TRY(plan_build_t<float>(dm, src, P, s));
+        TSP_CUDA(cudaStreamSynchronize(s));
         TSP_TRY(plan_col_range(dm, true, dm->deferredcoo_colidx.as<int>(), dm->coototal, P, s));
     }
 

@@ -33,6 +33,7 @@ struct tilespmv_plan
     // launch configuration of the persistent kernel
     int grid = 0, block = 0, smem = 0, ctas_per_sm = 0, sm_count = 0, stages = 0, max_warps = 0;
     int flags = 0;            // TILESPMV_PLAN_*
+    int format_mask = 0;      // formats this plan covers (bit f = TILESPMV_FMT_*, bit 1 = the extracted side entries); 0 = all
     // plans made mostly of extracted (side) entries are bound by scattered x gathers, and every gather in flight
     // pins a line of L1: such plans keep their shared memory under gather_smem_cap so that the SM's 256 KB are
     // carved into a larger L1 (uniform 1 M x 20: 176 us with 223 KB of shared memory, 122 us with 158 KB)
