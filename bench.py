@@ -38,6 +38,7 @@ METRIC = "fp64 SpMV GFLOP/s (2*nnz/t)"
 UNIT = "GFLOP/s"
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 NVLINK_PEER_GBS = 770.0    # measured peer copy per direction (B200_PROFILING.md)
+MODES = ("nccl", "fused", "pipelined", "halo")
 SEGMENT = 50               # x <- A*x restarts from x0 every SEGMENT iterations (keeps the iterates finite for any K)
 
 
@@ -543,7 +544,7 @@ def run_multi(args, rank, world, local_rank):
         xr, br = torch.cat(parts), torch.cat(bparts)
     del A, Aabs, y_chk, bound, parts, bparts
     verify, xs = {}, {}
-    for mode in ("nccl", "fused", "pipelined"):
+    for mode in MODES:
         try:
             xs[mode] = result(sp.iterate(x0.data_ptr(), KV, mode=mode, stream=stream))
             sp.sync(stream)
@@ -553,7 +554,7 @@ def run_multi(args, rank, world, local_rank):
             verify[mode] = {"max_err_over_bound": err, "ok": err <= 1e-10, "identical_on_all_ranks": bool(torch.equal(same, xs[mode]))}
         except Exception as e:
             verify[mode] = {"ok": False, "error": str(e)[:300]}
-    ref_mode = next((mo for mo in ("nccl", "fused", "pipelined") if mo in xs), None)
+    ref_mode = next((mo for mo in MODES if mo in xs), None)
     for mode in xs:
         verify[mode]["bitwise_equal_to_" + ref_mode] = bool(torch.equal(xs[mode], xs[ref_mode]))
     for mode in verify:  # a rank-local failure fails the mode everywhere
@@ -562,7 +563,7 @@ def run_multi(args, rank, world, local_rank):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         verify[mode]["verified"] = bool(flag.item())
     del xs, xr, br
-    good = [mo for mo in ("pipelined", "fused", "nccl") if verify[mo].get("verified")]
+    good = [mo for mo in MODES if verify[mo].get("verified")]
     if not good or not ok_spmv:
         if rank == 0:
             sys.stderr.write(f"bench: verification failed: spmv {ok_spmv}, {json.dumps(verify)}\n")
@@ -584,7 +585,7 @@ def run_multi(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
         nvl = nvlink_kib(gpu_index(local_rank))
-    for mode in [mo for mo in ("nccl", "fused", "pipelined") if mo in good]:
+    for mode in good:
         steps = args.steps
         run_iters(mode, args.warmup)
         sp.sync(stream)
@@ -786,6 +787,8 @@ def run_multi(args, rank, world, local_rank):
                                         "fused": "SpMV epilogue stores y into every peer's next x (P2P over NVLink) + 1 flag barrier",
                                         "pipelined": "copy-engine pushes of the y slice to each peer in the order of need + per-launch waits on "
                                                      "only the slices a launch reads (x panels cut at the ranks' row blocks)",
+                                        "halo": ("fused stores of only the rows a peer's next launch reads + copy-engine replication of the rest of "
+                                                 "every slice in the background" if info.halo_eligible else "not eligible for this matrix: ran as pipelined"),
                                         "allgather_bytes_in_per_gpu": (n - m) * 8, "allgather_bytes_out_per_gpu_unicast": (world - 1) * m * 8,
                                         "nvlink_floor_ms_unoverlapped": (n - m) * 8 / (NVLINK_PEER_GBS * 1e6)}),
             "spmv_no_exchange": {"ms_per_step": ms_spmv, "value": 2.0 * nnz_total / (ms_spmv * 1e-3) / 1e9,
@@ -829,7 +832,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)   # WARMUP_NUM (common.h:20-22)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c3", "c5"])
-    ap.add_argument("--exchange", default="pipelined", choices=["pipelined", "fused", "nccl"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "pipelined", "halo", "fused", "nccl"])
     ap.add_argument("--grid", type=int, default=160)
     ap.add_argument("--c3-rows", type=int, default=8_000_000)
     ap.add_argument("--c5-rows", type=int, default=50_000_000)

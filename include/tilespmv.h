@@ -321,6 +321,12 @@ int tilespmv_plan_set_peers(tilespmv_plan *plan, int npeers, void *const *peer_x
  *   TILESPMV_EXCHANGE_PIPELINED  copy engines push the slice to the peers in the order they need it; every launch of the
  *                                next iteration waits only for the slices its columns read (x panels cut at the row blocks
  *                                of the ranks, own panel first), so the exchange runs under the next iteration's compute
+ *   TILESPMV_EXCHANGE_HALO       for matrices whose row blocks read only a small window of x beyond their own slice (bands,
+ *                                stencils): the kernel's epilogue stores just the rows a peer's next launch reads into that
+ *                                peer's next x, a flag exchange with those neighbours orders the iterations, and the copy
+ *                                engines replicate the rest of every slice in the background (still a full all-gather of x
+ *                                per iteration, complete on every rank when the call ends).  Falls back to PIPELINED when
+ *                                some rank would have to store more than half of its slice that way.
  * All ranks must make the same sequence of calls with the same niters / exchange.  A tilespmv_dist must be destroyed
  * before its communicator (destroy is collective too).
  */
@@ -331,6 +337,7 @@ typedef struct tilespmv_dist tilespmv_dist;
 #define TILESPMV_EXCHANGE_NCCL 0
 #define TILESPMV_EXCHANGE_FUSED 1
 #define TILESPMV_EXCHANGE_PIPELINED 2
+#define TILESPMV_EXCHANGE_HALO 3
 int tilespmv_comm_create(const char *name, int rank, int nranks, unsigned flags, tilespmv_comm **out);
 void tilespmv_comm_destroy(tilespmv_comm *comm);
 int tilespmv_comm_barrier(tilespmv_comm *comm); /* host barrier over all ranks */
@@ -350,6 +357,8 @@ typedef struct
     int launch_units;        /* kernel launches per SpMV that can wait for different slices of x   */
     int equal_slices;        /* all row blocks have the same length (NCCL: one ncclAllGather)      */
     uint32_t unit_deps[64];  /* per launch unit: bit mask of the ranks whose slices of x it reads  */
+    int halo_eligible;       /* TILESPMV_EXCHANGE_HALO applies (else it runs PIPELINED)            */
+    int64_t need_lo, need_hi; /* x columns [need_lo, need_hi) this rank's launches read             */
 } tilespmv_dist_info;
 int tilespmv_dist_get_info(const tilespmv_dist *dist, tilespmv_dist_info *info);
 

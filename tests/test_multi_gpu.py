@@ -13,7 +13,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-MODES_ALL = ("nccl", "fused", "pipelined")
+MODES_ALL = ("nccl", "fused", "pipelined", "halo")
 
 
 def _worker(rank, world, name, case, K, ndev, q):
@@ -32,7 +32,7 @@ def _worker(rank, world, name, case, K, ndev, q):
         sp.spmv(x0.data_ptr(), y.data_ptr())  # single SpMV, no communication
         torch.cuda.synchronize()
         info = sp.info()
-        out = {"rows": sp.rows, "y": y[: sp.m_local].cpu().numpy(), "units": info.launch_units,
+        out = {"rows": sp.rows, "y": y[: sp.m_local].cpu().numpy(), "units": info.launch_units, "halo": bool(info.halo_eligible),
                "deps": [int(info.unit_deps[u]) for u in range(info.launch_units)]}
         for mode in MODES_ALL if use_nccl else MODES_ALL[1:]:
             ptr = sp.iterate(x0.data_ptr(), K, mode=mode)
@@ -116,6 +116,8 @@ def test_sharded_spmv_and_repeated_spmv(case, world):
         for r in range(world):
             assert res[r]["units"] == world
             assert res[r]["deps"] == [0 if u == 0 else 1 << ((r + u) % world) for u in range(world)], res[r]["deps"]
+    # bands and stencils read a small window of x beyond their own rows: the halo exchange applies; hubs / uniform do not
+    assert all(res[r]["halo"] == (case[0] in ("banded", "lap3d27")) for r in range(world)), [res[r]["halo"] for r in range(world)]
     # repeated SpMV: every rank ends with the same replicated x, equal to the CPU loop; the exchanges agree bitwise
     x, bound, want = x0.copy(), np.abs(x0), {}
     for k in range(K + 2):
@@ -123,7 +125,7 @@ def test_sharded_spmv_and_repeated_spmv(case, world):
         x = ora.csr_spmv(m, rp, ci, v, x)
         want[k + 1] = (x.copy(), bound.copy())
     modes = [mo for mo in MODES_ALL if mo in res[0]]
-    assert "pipelined" in modes and "fused" in modes
+    assert "pipelined" in modes and "fused" in modes and "halo" in modes
     for mode in modes:
         for key, k in ((mode, K), (mode + "+2", K + 2)):
             xr, br = want[k]

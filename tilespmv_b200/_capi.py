@@ -69,12 +69,13 @@ class PlanOptions(C.Structure):
 class DistInfo(C.Structure):
     _fields_ = [("rank", C.c_int), ("nranks", C.c_int), ("row0", C.c_int64), ("rows", C.c_int64),
                 ("slice_bytes", C.c_int64), ("device_bytes", C.c_int64), ("launch_units", C.c_int),
-                ("equal_slices", C.c_int), ("unit_deps", C.c_uint32 * 64)]
+                ("equal_slices", C.c_int), ("unit_deps", C.c_uint32 * 64), ("halo_eligible", C.c_int),
+                ("need_lo", C.c_int64), ("need_hi", C.c_int64)]
 
 
 COMM_NCCL = 1
 DIST_UNIFORM_PANELS = 1
-EXCHANGE_NCCL, EXCHANGE_FUSED, EXCHANGE_PIPELINED = 0, 1, 2
+EXCHANGE_NCCL, EXCHANGE_FUSED, EXCHANGE_PIPELINED, EXCHANGE_HALO = 0, 1, 2, 3
 
 
 class PlanInfo(C.Structure):

@@ -1335,7 +1335,11 @@ int tilespmv_plan_set_peers(tilespmv_plan *plan, int npeers, void *const *peer_x
     plan->npeers = npeers;
     plan->row_offset = row_offset;
     for (int p = 0; p < TSP_MAX_PEERS; p++)
+    {
         plan->peers[p] = p < npeers ? peer_x[p] : nullptr;
+        plan->peer_lo[p] = 0;
+        plan->peer_hi[p] = p < npeers ? (int64_t)1 << 62 : 0; // every row
+    }
     return TILESPMV_OK;
 }
 

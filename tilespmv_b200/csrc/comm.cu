@@ -98,6 +98,11 @@ struct tilespmv_dist
     uint32_t epoch = 1; // next unused epoch (flags start at 0)
     int cur = 0;        // x buffer holding the current x
     std::vector<uint32_t> deps; // per launch unit: bit mask of the source ranks whose slices it reads (self excluded)
+    // halo exchange: need[r] = the x columns rank r's launches read; rank p fuse-stores its rows inside need[q] to q and the
+    // copy engines replicate the rest in the background.  Eligible when no rank sends more than half of its slice that way.
+    std::vector<long long> need_lo, need_hi;
+    bool halo_ok = false;
+    uint32_t halo_in = 0, halo_out = 0; // peers whose rows I read / peers that read my rows
     unsigned long long spin_timeout_ns = 30ull * 1000000000ull;
     // TILESPMV_DIST_DEBUG=1: CUDA-event timing of the LAST push of every pipelined call, printed by tilespmv_dist_sync
     bool debug = false, dbg_armed = false;
@@ -482,6 +487,23 @@ static int dist_create(tilespmv_comm *c, const tilespmv_dmat *dm, const int64_t 
                 d->deps[(size_t)u] |= 1u << r;
     }
 
+    d->need_lo.assign((size_t)R, 0);
+    d->need_hi.assign((size_t)R, 0);
+    {
+        long long lo = d->n, hi = 0;
+        for (int u = 0; u < nunits; u++)
+        {
+            const tilespmv_plan *Q = u == 0 ? d->plan : d->plan->sub[(size_t)u - 1];
+            if (Q->xcol_hi > Q->xcol_lo)
+            {
+                lo = std::min(lo, Q->xcol_lo);
+                hi = std::max(hi, Q->xcol_hi);
+            }
+        }
+        d->need_lo[(size_t)me] = hi > lo ? lo : 0;
+        d->need_hi[(size_t)me] = hi > lo ? hi : 0;
+    }
+
     // ---- one block: flags | x buffer 0 | x buffer 1, mapped by every peer through CUDA IPC ----
     d->xbytes = ((size_t)d->n * (size_t)d->vs + 255u) & ~(size_t)255u;
     d->x_off[0] = DIST_FLAG_BYTES;
@@ -507,6 +529,8 @@ static int dist_create(tilespmv_comm *c, const tilespmv_dmat *dm, const int64_t 
         mine.device = c->device;
         mine.pid = (int)getpid();
         mine.aux[0] = (long long)(DIST_FLAG_BYTES + 2 * d->xbytes);
+        mine.aux[1] = d->need_lo[(size_t)me];
+        mine.aux[2] = d->need_hi[(size_t)me];
         rc = comm_barrier(c);
         if (rc != TILESPMV_OK)
             return fail(rc);
@@ -553,10 +577,32 @@ static int dist_create(tilespmv_comm *c, const tilespmv_dmat *dm, const int64_t 
             d->peer_block[r] = static_cast<unsigned char *>(p);
             d->peer_mapped[r] = true;
             d->peer_device[r] = o.device;
+            d->need_lo[(size_t)r] = o.aux[1];
+            d->need_hi[(size_t)r] = o.aux[2];
         }
         rc = comm_barrier(c); // every rank has read every slot: the slots may be re-used by the next dist_create
         if (rc != TILESPMV_OK)
             return fail(rc);
+    }
+    // halo eligibility (the same verdict on every rank: it only uses the published ranges and the cuts)
+    d->halo_ok = R > 1;
+    for (int p = 0; p < R && d->halo_ok; p++)
+    {
+        long long sent = 0;
+        for (int q = 0; q < R; q++)
+            if (q != p)
+                sent += std::max(0ll, std::min(d->need_hi[(size_t)q], (long long)row_cuts[p + 1]) - std::max(d->need_lo[(size_t)q], (long long)row_cuts[p]));
+        if (2 * sent > (long long)(row_cuts[p + 1] - row_cuts[p]))
+            d->halo_ok = false;
+    }
+    for (int q = 0; q < R; q++)
+    {
+        if (q == me)
+            continue;
+        if (std::min(d->need_hi[(size_t)q], (long long)row_cuts[me + 1]) > std::max(d->need_lo[(size_t)q], (long long)row_cuts[me]))
+            d->halo_out |= 1u << q;
+        if (std::min(d->need_hi[(size_t)me], (long long)row_cuts[q + 1]) > std::max(d->need_lo[(size_t)me], (long long)row_cuts[q]))
+            d->halo_in |= 1u << q;
     }
     if (const char *e = getenv("TILESPMV_DIST_DEBUG"))
         d->debug = atoi(e) != 0;
@@ -713,6 +759,88 @@ static int iterate_pipelined(tilespmv_dist *d, int niters, cudaStream_t s)
     return TILESPMV_OK;
 }
 
+// FUSED for the rows a peer reads next (its halo) + PIPELINED for everything else: the kernel's epilogue stores the
+// rows inside need[q] straight into q's next x, one flag exchange with the halo neighbours orders the iterations, and
+// the copy engines push the rest of the slice to every peer in the background (nobody reads it before the call ends,
+// where every rank waits for all slices).  Falls back to the pipelined exchange when the halos are not small.
+static int iterate_halo(tilespmv_dist *d, int niters, cudaStream_t s)
+{
+    if (!d->halo_ok)
+        return iterate_pipelined(d, niters, s);
+    const uint32_t peers = all_peers_mask(d), E0 = d->epoch;
+    const int R = d->nranks, me = d->rank;
+    const size_t vs = (size_t)d->vs, slice_off = (size_t)d->r0 * vs;
+    d->ev_push_valid[0] = d->ev_push_valid[1] = false;
+    // local rows of mine that peer q reads: [out_lo, out_hi)
+    long long out_lo[COMM_MAX_RANKS], out_hi[COMM_MAX_RANKS];
+    for (int q = 0; q < R; q++)
+    {
+        out_lo[q] = std::max(d->need_lo[(size_t)q], d->r0) - d->r0;
+        out_hi[q] = std::max(out_lo[q], std::min(d->need_hi[(size_t)q], d->r0 + d->m_local) - d->r0);
+        if (q == me)
+            out_lo[q] = out_hi[q] = 0;
+    }
+    const uint32_t nb = d->halo_in | d->halo_out;
+    TSP_TRY(flag_signal(d, DIST_OFF_A, peers, E0, s)); // entered the call
+    for (int i = 0; i < niters; i++)
+    {
+        const uint32_t e = E0 + (uint32_t)i;
+        const int sb = (d->cur + i) & 1, db = sb ^ 1;
+        void *pp[TSP_MAX_PEERS];
+        int np = 0;
+        tilespmv_plan *P = d->plan;
+        for (int q = 0; q < R; q++)
+            if ((d->halo_out >> q) & 1u)
+            {
+                pp[np] = xbuf(d, q, db);
+                P->peer_lo[np] = out_lo[q];
+                P->peer_hi[np] = out_hi[q];
+                np++;
+            }
+        P->npeers = np;
+        P->row_offset = d->r0;
+        for (int k = 0; k < TSP_MAX_PEERS; k++)
+            P->peers[k] = k < np ? pp[k] : nullptr;
+        // the halo neighbours have finished epoch e - 1: their halo stores into my src buffer have landed and they no
+        // longer read the buffer this epoch's stores go to
+        TSP_TRY(flag_wait(d, DIST_OFF_A, nb, e, s));
+        if (d->ev_push_valid[i & 1]) // the background pushes of iteration i - 2 read the slice this iteration overwrites
+            TSP_CUDA(cudaStreamWaitEvent(s, d->ev_push[i & 1], 0));
+        TSP_TRY(launch_units(d, xbuf(d, me, sb), xbuf(d, me, db), s, true));
+        TSP_CUDA(cudaEventRecord(d->ev_kernel[i & 1], s));
+        TSP_TRY(flag_signal(d, DIST_OFF_A, peers, e + 1, s));
+        // ---- background replication of everything the kernel did not store itself ----
+        TSP_CUDA(cudaStreamWaitEvent(d->s_comm, d->ev_kernel[i & 1], 0));
+        for (int k = 1; k < R; k++)
+        {
+            const int dst = (me - k + R) % R;
+            TSP_TRY(flag_wait(d, DIST_OFF_A, 1u << dst, e, d->s_comm));
+            const long long seg[2][2] = {{0, out_lo[dst]}, {out_hi[dst], d->m_local}};
+            for (int g = 0; g < 2; g++)
+                if (seg[g][1] > seg[g][0])
+                    TSP_CUDA(cudaMemcpyPeerAsync(xbuf(d, dst, db) + slice_off + (size_t)seg[g][0] * vs, d->peer_device[dst],
+                                                 xbuf(d, me, db) + slice_off + (size_t)seg[g][0] * vs, d->comm->device,
+                                                 (size_t)(seg[g][1] - seg[g][0]) * vs, d->s_comm));
+            TSP_TRY(flag_signal(d, DIST_OFF_D, 1u << dst, e + 1, d->s_comm));
+        }
+        TSP_CUDA(cudaEventRecord(d->ev_push[i & 1], d->s_comm));
+        d->ev_push_valid[i & 1] = true;
+    }
+    // the final x is complete on this rank: halo stores (neighbours finished the last epoch) + every background slice
+    if (niters > 0)
+    {
+        TSP_TRY(flag_wait(d, DIST_OFF_A, nb, E0 + (uint32_t)niters, s));
+        TSP_TRY(flag_wait(d, DIST_OFF_D, peers, E0 + (uint32_t)niters, s));
+    }
+    for (int b = 0; b < 2; b++)
+        if (d->ev_push_valid[b])
+            TSP_CUDA(cudaStreamWaitEvent(s, d->ev_push[b], 0));
+    tilespmv_plan_set_peers(d->plan, 0, nullptr, 0);
+    d->epoch = E0 + (uint32_t)niters + 1;
+    d->cur = (d->cur + niters) & 1;
+    return TILESPMV_OK;
+}
+
 } // namespace tsp
 
 using namespace tsp;
@@ -780,6 +908,8 @@ int tilespmv_dist_iterate(tilespmv_dist *dist, const void *d_x0, int niters, int
         return iterate_fused(dist, niters, s);
     if (exchange == TILESPMV_EXCHANGE_PIPELINED)
         return iterate_pipelined(dist, niters, s);
+    if (exchange == TILESPMV_EXCHANGE_HALO)
+        return iterate_halo(dist, niters, s);
     set_error("dist_iterate: unknown exchange %d", exchange);
     return TILESPMV_ERR_INVALID;
 }
@@ -842,6 +972,9 @@ int tilespmv_dist_get_info(const tilespmv_dist *dist, tilespmv_dist_info *info)
     for (int u = 0; u < info->launch_units && u < 64; u++)
         info->unit_deps[u] = dist->deps[(size_t)u];
     info->slice_bytes = dist->m_local * dist->vs;
+    info->halo_eligible = dist->halo_ok ? 1 : 0;
+    info->need_lo = dist->need_lo[(size_t)dist->rank];
+    info->need_hi = dist->need_hi[(size_t)dist->rank];
     info->device_bytes = (int64_t)dist->block.bytes + dist->plan->device_bytes();
     return TILESPMV_OK;
 }

@@ -60,6 +60,7 @@ struct tilespmv_plan
     int npeers = 0;
     void *peers[TSP_MAX_PEERS] = {nullptr};
     int64_t row_offset = 0;
+    int64_t peer_lo[TSP_MAX_PEERS] = {0}, peer_hi[TSP_MAX_PEERS] = {0}; // local rows peer q receives (set_peers: all)
 
     // device staging for the host-pointer entry point
     tsp::DevBuf hx, hy;

@@ -218,6 +218,9 @@ struct SpmvArgs
     int accumulate; // y += A*x (column-panel sub-plans) instead of y = A*x
     long long row_offset;
     T *peers[TSP_MAX_PEERS];
+    // peer q receives the local rows [peer_lo[q], peer_hi[q]) only: everything for the plain fused exchange, just the rows
+    // its next launch reads (the halo) when the copy engines replicate the rest in the background (comm.cu)
+    long long peer_lo[TSP_MAX_PEERS], peer_hi[TSP_MAX_PEERS];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -708,8 +711,9 @@ __device__ __forceinline__ void process_chunk(const unsigned char *st, uint32_t 
                         acc += a.y[row];
                     (partial ? a.scratch : a.y)[row] = acc;
                     if (!partial)
-                        for (int q = 0; q < a.npeers; q++) // fused all-gather: next x of every peer
-                            a.peers[q][a.row_offset + (long long)row] = acc;
+                        for (int q = 0; q < a.npeers; q++) // fused all-gather: next x of every peer that wants this row
+                            if ((long long)row >= a.peer_lo[q] && (long long)row < a.peer_hi[q])
+                                a.peers[q][a.row_offset + (long long)row] = acc;
                 }
             }
         }
@@ -839,7 +843,8 @@ __global__ void __launch_bounds__(128)
         sum += y[row];
     y[row] = sum;
     for (int p = 0; p < npeers; p++)
-        a.peers[p][row_offset + (long long)row] = sum;
+        if ((long long)row >= a.peer_lo[p] && (long long)row < a.peer_hi[p])
+            a.peers[p][row_offset + (long long)row] = sum;
 }
 
 // the same for rows cut into many pieces: one CTA per row, 16 slot lanes x 16 rows, fixed-order
@@ -876,7 +881,8 @@ __global__ void __launch_bounds__(256)
             sum += y[row];
         y[row] = sum;
         for (int p = 0; p < npeers; p++)
-            a.peers[p][row_offset + (long long)row] = sum;
+            if ((long long)row >= a.peer_lo[p] && (long long)row < a.peer_hi[p])
+                a.peers[p][row_offset + (long long)row] = sum;
     }
 }
 
@@ -970,7 +976,8 @@ int spmv_configure(tilespmv_plan *P)
 }
 
 template <class T>
-static int plan_launch_one(tilespmv_plan *P, const T *x, T *y, cudaStream_t s, int npeers, void *const *peers, int64_t row_offset)
+static int plan_launch_one(tilespmv_plan *P, const T *x, T *y, cudaStream_t s, int npeers, void *const *peers, int64_t row_offset,
+                           const int64_t *peer_lo, const int64_t *peer_hi)
 {
     if (P->nchunks == 0)
         return TILESPMV_OK;
@@ -990,7 +997,11 @@ static int plan_launch_one(tilespmv_plan *P, const T *x, T *y, cudaStream_t s, i
     a.accumulate = P->accumulate ? 1 : 0;
     a.row_offset = row_offset;
     for (int p = 0; p < TSP_MAX_PEERS; p++)
+    {
         a.peers[p] = p < npeers ? reinterpret_cast<T *>(peers[p]) : nullptr;
+        a.peer_lo[p] = p < npeers ? peer_lo[p] : 0;
+        a.peer_hi[p] = p < npeers ? peer_hi[p] : 0;
+    }
     const int grid = P->grid; // fixed at plan time: the stream's lookahead lists depend on it
     {
         void *args[] = {(void *)&a};
@@ -1020,11 +1031,11 @@ template <class T>
 static int plan_launch_t(tilespmv_plan *P, const T *x, T *y, cudaStream_t s)
 {
     const bool alone = P->sub.empty();
-    TSP_TRY(plan_launch_one<T>(P, x, y, s, alone ? P->npeers : 0, P->peers, P->row_offset));
+    TSP_TRY(plan_launch_one<T>(P, x, y, s, alone ? P->npeers : 0, P->peers, P->row_offset, P->peer_lo, P->peer_hi));
     for (size_t i = 0; i < P->sub.size(); i++)
     {
         const bool last = i + 1 == P->sub.size();
-        TSP_TRY(plan_launch_one<T>(P->sub[i], x, y, s, last ? P->npeers : 0, P->peers, P->row_offset));
+        TSP_TRY(plan_launch_one<T>(P->sub[i], x, y, s, last ? P->npeers : 0, P->peers, P->row_offset, P->peer_lo, P->peer_hi));
     }
     return TILESPMV_OK;
 }
@@ -1051,8 +1062,9 @@ int plan_launch_unit(tilespmv_plan *P, int unit, const void *d_x, void *d_y, cud
     tilespmv_plan *Q = unit == 0 ? P : P->sub[(size_t)unit - 1];
     const int np = with_peers ? P->npeers : 0;
     if (P->precision == 8)
-        return plan_launch_one<double>(Q, static_cast<const double *>(d_x), static_cast<double *>(d_y), s, np, P->peers, P->row_offset);
-    return plan_launch_one<float>(Q, static_cast<const float *>(d_x), static_cast<float *>(d_y), s, np, P->peers, P->row_offset);
+        return plan_launch_one<double>(Q, static_cast<const double *>(d_x), static_cast<double *>(d_y), s, np, P->peers, P->row_offset, P->peer_lo,
+                                       P->peer_hi);
+    return plan_launch_one<float>(Q, static_cast<const float *>(d_x), static_cast<float *>(d_y), s, np, P->peers, P->row_offset, P->peer_lo, P->peer_hi);
 }
 
 } // namespace tsp

@@ -7,6 +7,7 @@ CUDA-IPC-mapped x buffers, the NCCL communicator and the three exchanges of the 
   "nccl"       SpMV, then ncclAllGather / grouped ncclBroadcast            (baseline)
   "fused"      the kernel's epilogue stores y into every peer's next x      (NVLink P2P stores)
   "pipelined"  copy-engine pushes ordered by need + per-launch waits        (exchange hidden under the next iteration)
+  "halo"       fused stores of the rows a peer reads next + copy-engine replication of the rest (bands, stencils)
 
 Nothing here needs torch: device pointers are plain ints.  torch shows up only in callers that want tensors.
 """
@@ -17,7 +18,8 @@ import numpy as np
 
 from . import _capi, api, sharding
 
-EXCHANGES = {"nccl": _capi.EXCHANGE_NCCL, "fused": _capi.EXCHANGE_FUSED, "pipelined": _capi.EXCHANGE_PIPELINED}
+EXCHANGES = {"nccl": _capi.EXCHANGE_NCCL, "fused": _capi.EXCHANGE_FUSED, "pipelined": _capi.EXCHANGE_PIPELINED,
+             "halo": _capi.EXCHANGE_HALO}
 
 
 class Comm:
