@@ -32,7 +32,7 @@ def _worker(rank, world, name, case, K, ndev, q):
         sp.spmv(x0.data_ptr(), y.data_ptr())  # single SpMV, no communication
         torch.cuda.synchronize()
         info = sp.info()
-        out = {"rows": sp.rows, "y": y[: sp.m_local].cpu().numpy(), "units": info.launch_units, "halo": bool(info.halo_eligible),
+        out = {"rows": sp.rows, "y": y[: sp.m_local].cpu().numpy(), "units": info.launch_units, "halo_ok": bool(info.halo_eligible),
                "deps": [int(info.unit_deps[u]) for u in range(info.launch_units)]}
         for mode in MODES_ALL if use_nccl else MODES_ALL[1:]:
             ptr = sp.iterate(x0.data_ptr(), K, mode=mode)
@@ -117,7 +117,7 @@ def test_sharded_spmv_and_repeated_spmv(case, world):
             assert res[r]["units"] == world
             assert res[r]["deps"] == [0 if u == 0 else 1 << ((r + u) % world) for u in range(world)], res[r]["deps"]
     # bands and stencils read a small window of x beyond their own rows: the halo exchange applies; hubs / uniform do not
-    assert all(res[r]["halo"] == (case[0] in ("banded", "lap3d27")) for r in range(world)), [res[r]["halo"] for r in range(world)]
+    assert all(res[r]["halo_ok"] == (case[0] in ("banded", "lap3d27")) for r in range(world)), [res[r]["halo_ok"] for r in range(world)]
     # repeated SpMV: every rank ends with the same replicated x, equal to the CPU loop; the exchanges agree bitwise
     x, bound, want = x0.copy(), np.abs(x0), {}
     for k in range(K + 2):

@@ -105,7 +105,7 @@ _lib = None
 
 
 def lib_path():
-    return build.LIB_CUDA
+    return os.environ.get("TILESPMV_LIB_PATH") or build.LIB_CUDA
 
 
 def load(rebuild=False):
@@ -113,10 +113,11 @@ def load(rebuild=False):
     global _lib
     if _lib is not None and not rebuild:
         return _lib
-    path = build.LIB_CUDA
-    # build_cuda() is a no-op unless a source is newer than the .so: a stale binary whose struct layouts differ from
-    # the ctypes mirrors below must never be loaded silently
-    build.build_cuda(force=rebuild)
+    path = os.environ.get("TILESPMV_LIB_PATH") or build.LIB_CUDA  # the override is for A/B runs of two builds on one box
+    # build_cuda() is a no-op unless a source differs from what the .so was built from: a stale binary whose struct
+    # layouts differ from the ctypes mirrors below must never be loaded silently
+    if path == build.LIB_CUDA:
+        build.build_cuda(force=rebuild)
     if not os.path.exists(path):
         raise RuntimeError("libtilespmv_b200.so is missing and could not be built; there is no CPU fallback")
     _preload_nccl()
