@@ -257,6 +257,12 @@ typedef struct
  * byte-balanced chunk schedule.  opts may be NULL. */
 int tilespmv_plan_create(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tilespmv_plan **out);
 void tilespmv_plan_destroy(tilespmv_plan *plan);
+/* Binary cache of a packed plan (incl. its x-panel sub-plans): a later run loads it instead of converting and planning
+ * again (the reference re-converts and re-uploads the matrix on every run, tilespmv_cuda.h:794-1056).  The file is tied
+ * to the launch shape it was packed for: tilespmv_plan_load returns TILESPMV_ERR_UNSUPPORTED on a GPU with another SM
+ * count / shared-memory size (plan again), TILESPMV_ERR_IO for a missing, truncated or corrupt file (checksummed). */
+int tilespmv_plan_save(const tilespmv_plan *plan, const char *path);
+int tilespmv_plan_load(const char *path, tilespmv_plan **out);
 
 /* y = A*x with DEVICE pointers (16-byte aligned), asynchronous on `stream` (a cudaStream_t
  * passed as void*; NULL = default stream).  x has colA entries, y has rowA entries. */

@@ -378,3 +378,37 @@ def test_single_format_plans_partition_the_matrix(name):
         present = info.tiles_by_format[f] > 0 or (f == 1 and info.nnz_side > 0)
         assert (ms[f] > 0) == present and (nnz[f] > 0) == present
     assert ms[7] > 0 and ms[8] > 0
+
+
+# ---- binary cache of the packed plan ----
+@pytest.mark.parametrize("name,kw", [("seven_formats", {}), ("banded_8k_real", {}), ("hub_rows", {}), ("rmat_12_real", dict(xpanel_bytes=8192))])
+def test_plan_cache_round_trip(tmp_path, name, kw):
+    """tilespmv_plan_save / tilespmv_plan_load: the loaded plan (with its x-panel sub-plans and split rows) gives the
+    same y bit for bit without the Tile_matrix; corrupt or foreign files are refused."""
+    m, n, rp, ci, v = CASES[name]()
+    x = x_for(n, 0)
+    dm = api.DeviceTileMatrix.from_csr(m, n, rp, ci, v)
+    plan = api.Plan(dm, **kw)
+    y = plan.spmv_host(x)
+    path = str(tmp_path / "plan.bin")
+    plan.save(path)
+    i0 = plan.info()
+    plan.destroy()
+    dm.destroy()
+    loaded = api.Plan.load(path, api.F64, m, n)
+    i1 = loaded.info()
+    assert (i1.nchunks, i1.stream_bytes, i1.split_rows, i1.xpanels, i1.launches_per_spmv, i1.algorithmic_bytes) == \
+           (i0.nchunks, i0.stream_bytes, i0.split_rows, i0.xpanels, i0.launches_per_spmv, i0.algorithmic_bytes)
+    assert loaded.spmv_host(x).tobytes() == y.tobytes()
+    assert loaded.spmv_host(2 * x).tobytes() == (2 * y).tobytes()
+    blob = bytearray(open(path, "rb").read())
+    blob[len(blob) // 2] ^= 0x5a
+    bad = str(tmp_path / "bad.bin")
+    open(bad, "wb").write(bytes(blob))
+    with pytest.raises(api.TileSpMVError):
+        api.Plan.load(bad, api.F64, m, n)
+    open(bad, "wb").write(bytes(blob[: len(blob) // 3]))
+    with pytest.raises(api.TileSpMVError):
+        api.Plan.load(bad, api.F64, m, n)
+    with pytest.raises(api.TileSpMVError):
+        api.Plan.load(str(tmp_path / "missing.bin"), api.F64, m, n)

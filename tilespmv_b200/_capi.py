@@ -92,7 +92,7 @@ EXPORTS = [
     "tilespmv_prepare_f64", "tilespmv_prepare_f32", "call_tilespmv_cuda_f64", "call_tilespmv_cuda_f32",
     "tilespmv_convert", "tilespmv_dmat_upload_f64", "tilespmv_dmat_upload_f32",
     "tilespmv_dmat_export_f64", "tilespmv_dmat_export_f32", "tilespmv_dmat_destroy",
-    "tilespmv_dmat_get_info", "tilespmv_plan_create", "tilespmv_plan_destroy", "tilespmv_plan_spmv",
+    "tilespmv_dmat_get_info", "tilespmv_plan_create", "tilespmv_plan_destroy", "tilespmv_plan_save", "tilespmv_plan_load", "tilespmv_plan_spmv",
     "tilespmv_plan_spmv_host", "tilespmv_plan_spmv_host_batch", "tilespmv_plan_iterate", "tilespmv_partition_rows", "tilespmv_plan_set_peers", "tilespmv_plan_get_info", "tilespmv_plan_time", "tilespmv_format_profile",
     "tilespmv_mmio_allinone_f64", "tilespmv_mmio_allinone_f32", "tilespmv_last_error",
     "tilespmv_version", "tilespmv_kernel_launch_count",
@@ -141,6 +141,8 @@ def load(rebuild=False):
     L.tilespmv_plan_set_peers.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int64]
     L.tilespmv_plan_create.argtypes = [C.c_void_p, C.POINTER(PlanOptions), C.POINTER(C.c_void_p)]
     L.tilespmv_plan_destroy.argtypes = [C.c_void_p]
+    L.tilespmv_plan_save.argtypes = [C.c_void_p, C.c_char_p]
+    L.tilespmv_plan_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
     L.tilespmv_plan_get_info.argtypes = [C.c_void_p, C.POINTER(PlanInfo)]
     L.tilespmv_dmat_destroy.argtypes = [C.c_void_p]
     L.tilespmv_dmat_get_info.argtypes = [C.c_void_p, C.POINTER(DmatInfo)]

@@ -186,6 +186,20 @@ class Plan:
         self.rowA, self.colA = dmat.rowA, dmat.colA
         self.val_dtype = dmat.val_dtype
 
+    def save(self, path):
+        """tilespmv_plan_save: binary cache of the packed plan (and its x-panel sub-plans)."""
+        check(_capi.load().tilespmv_plan_save(self.handle, path.encode()), "tilespmv_plan_save")
+
+    @classmethod
+    def load(cls, path, precision, rowA, colA):
+        """tilespmv_plan_load: a plan saved on a GPU with the same SM count / shared memory; raises TileSpMVError otherwise."""
+        h = C.c_void_p()
+        check(_capi.load().tilespmv_plan_load(path.encode(), C.byref(h)), "tilespmv_plan_load")
+        self = cls.__new__(cls)
+        self.handle, self.precision, self.rowA, self.colA = h, precision, rowA, colA
+        self.val_dtype = np.float64 if precision == F64 else np.float32
+        return self
+
     def info(self):
         i = _capi.PlanInfo()
         check(_capi.load().tilespmv_plan_get_info(self.handle, C.byref(i)), "tilespmv_plan_get_info")

@@ -1121,6 +1121,27 @@ int tilespmv_plan_create(const tilespmv_dmat *dm, const tilespmv_plan_options *o
     *out = P;
     return TILESPMV_OK;
 }
+int tilespmv_plan_save(const tilespmv_plan *plan, const char *path)
+{
+    clear_error();
+    if (!plan || !path)
+    {
+        set_error("plan_save: null argument");
+        return TILESPMV_ERR_INVALID;
+    }
+    return plan_save(plan, path);
+}
+int tilespmv_plan_load(const char *path, tilespmv_plan **out)
+{
+    clear_error();
+    if (!path || !out)
+    {
+        set_error("plan_load: null argument");
+        return TILESPMV_ERR_INVALID;
+    }
+    TSP_TRY(require_device());
+    return plan_load(path, out);
+}
 void tilespmv_plan_destroy(tilespmv_plan *plan) { delete plan; }
 
 int tilespmv_plan_spmv(tilespmv_plan *plan, const void *d_x, void *d_y, void *stream)

@@ -85,6 +85,27 @@ __global__ void __launch_bounds__(PL_THREADS) filter_format_kernel(int T, const 
         out[t] = ((mask >> (unsigned)fmt[t]) & 1u) ? fmt[t] : (char)TILESPMV_FMT_COO;
 }
 
+// the per-tile prefix sums of every block row that has to be cut into pieces, gathered into compact arrays so that the
+// host-side piece cutter needs ONE device-to-host copy (one small copy per hub row cost 1.5 s on R-MAT 2^24)
+__global__ void __launch_bounds__(PL_THREADS)
+    gather_long_rows_kernel(int nlong, const int *__restrict__ row_ta, const long long *__restrict__ row_off, const long long *__restrict__ ob,
+                            const int *__restrict__ nc, const int *__restrict__ oc, const int *__restrict__ ws, long long *__restrict__ c_ob,
+                            int *__restrict__ c_nc, int *__restrict__ c_oc, int *__restrict__ c_ws)
+{
+    const int i = blockIdx.x;
+    if (i >= nlong)
+        return;
+    const int ta = row_ta[i];
+    const long long o = row_off[i], cnt = row_off[i + 1] - o;
+    for (long long k = threadIdx.x; k < cnt; k += blockDim.x)
+    {
+        c_ob[o + k] = ob[ta + k];
+        c_nc[o + k] = nc[ta + k];
+        c_oc[o + k] = oc[ta + k];
+        c_ws[o + k] = ws[ta + k];
+    }
+}
+
 struct TileScans // all T+1 entries
 {
     const int *nc;        // stream tiles
@@ -872,27 +893,78 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
         acc = ChunkAcc();
     };
     chunk_item0.push_back(0);
+    // does block row b fit a chunk on its own?  (rows that do not are cut into pieces below)
+    auto row_fits_alone = [&](int b, ChunkAcc &one) {
+        const int ns = row_s0[b + 1] - row_s0[b];
+        const long long pay_ll = (long long)ell_group_bytes((uint32_t)row_nsr[b], vs) + row_other_bytes(b);
+        one = ChunkAcc();
+        one.nrows = 1;
+        one.ntiles = (uint32_t)row_nt[b];
+        one.nother = (uint32_t)row_other_count(b);
+        one.nside = (uint32_t)ns;
+        one.nsiderows = ns > 0 ? 1 : 0;
+        bool fits = pay_ll < (long long)C && row_nt[b] <= 256 && row_nsr[b] < 60000 && ns < (int)C;
+        if (fits)
+        {
+            one.payload = (uint32_t)pay_ll;
+            fits = one.bytes(vs) <= C && one.xbytes(vs) <= X;
+        }
+        return fits;
+    };
+    // per-tile prefix sums of all long rows that hold stream tiles, in one gather + one copy
     std::vector<long long> h_ob;
     std::vector<int> h_nc, h_oc, h_ws;
+    std::vector<long long> long_off; // per long row (in block-row order): offset into the compact arrays
+    {
+        std::vector<int> long_ta;
+        long_off.push_back(0);
+        for (int b = 0; b < tilem; b++)
+        {
+            const int ns = row_s0[b + 1] - row_s0[b];
+            if (!P->keep_all_rows && ns == 0 && row_nt[b] == 0)
+                continue;
+            ChunkAcc one;
+            if (row_nt[b] > 0 && !row_fits_alone(b, one))
+            {
+                long_ta.push_back(tile_ptr[b]);
+                long_off.push_back(long_off.back() + (tile_ptr[b + 1] - tile_ptr[b]) + 1);
+            }
+        }
+        const size_t nlong = long_ta.size(), total = (size_t)long_off.back();
+        if (nlong > 0)
+        {
+            DevBuf d_ta, d_off, c_ob, c_nc, c_oc, c_ws;
+            TSP_TRY(d_ta.alloc(nlong * sizeof(int), false));
+            TSP_TRY(d_off.alloc((nlong + 1) * sizeof(long long), false));
+            TSP_TRY(c_ob.alloc(total * sizeof(long long), false));
+            TSP_TRY(c_nc.alloc(total * sizeof(int), false));
+            TSP_TRY(c_oc.alloc(total * sizeof(int), false));
+            TSP_TRY(c_ws.alloc(total * sizeof(int), false));
+            TSP_CUDA(cudaMemcpyAsync(d_ta.p, long_ta.data(), nlong * sizeof(int), cudaMemcpyHostToDevice, s));
+            TSP_CUDA(cudaMemcpyAsync(d_off.p, long_off.data(), (nlong + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
+            TSP_LAUNCH(gather_long_rows_kernel, (unsigned)nlong, PL_THREADS, 0, s, (int)nlong, d_ta.as<int>(), d_off.as<long long>(),
+                       d_ob.as<long long>(), d_nc.as<int>(), d_oc.as<int>(), d_ws.as<int>(), c_ob.as<long long>(), c_nc.as<int>(),
+                       c_oc.as<int>(), c_ws.as<int>());
+            h_ob.resize(total);
+            h_nc.resize(total);
+            h_oc.resize(total);
+            h_ws.resize(total);
+            TSP_CUDA(cudaMemcpyAsync(h_ob.data(), c_ob.p, total * sizeof(long long), cudaMemcpyDeviceToHost, s));
+            TSP_CUDA(cudaMemcpyAsync(h_nc.data(), c_nc.p, total * sizeof(int), cudaMemcpyDeviceToHost, s));
+            TSP_CUDA(cudaMemcpyAsync(h_oc.data(), c_oc.p, total * sizeof(int), cudaMemcpyDeviceToHost, s));
+            TSP_CUDA(cudaMemcpyAsync(h_ws.data(), c_ws.p, total * sizeof(int), cudaMemcpyDeviceToHost, s));
+            TSP_CUDA(cudaStreamSynchronize(s));
+        }
+    }
+    size_t long_idx = 0;
     for (int b = 0; b < tilem; b++)
     {
         const int rowlen = b == tilem - 1 ? rowA - (tilem - 1) * TS : TS;
         const int ns = row_s0[b + 1] - row_s0[b];
         if (!P->keep_all_rows && ns == 0 && row_nt[b] == 0)
             continue; // an accumulating panel plan has nothing to add to this block row
-        const long long pay_ll = (long long)ell_group_bytes((uint32_t)row_nsr[b], vs) + row_other_bytes(b);
         ChunkAcc one;
-        one.nrows = 1;
-        one.ntiles = (uint32_t)row_nt[b];
-        one.nother = (uint32_t)row_other_count(b);
-        one.nside = (uint32_t)ns;
-        one.nsiderows = ns > 0 ? 1 : 0;
-        bool fits_alone = pay_ll < (long long)C && row_nt[b] <= 256 && row_nsr[b] < 60000 && ns < (int)C;
-        if (fits_alone)
-        {
-            one.payload = (uint32_t)pay_ll;
-            fits_alone = one.bytes(vs) <= C && one.xbytes(vs) <= X;
-        }
+        const bool fits_alone = row_fits_alone(b, one);
         if (fits_alone)
         {
             ChunkAcc trial = acc;
@@ -915,21 +987,15 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
         }
         // ---- long block row: cut into pieces, each piece is its own chunk ----
         close_chunk();
-        const int ta = tile_ptr[b], tb = tile_ptr[b + 1];
+        const int tb = tile_ptr[b + 1];
+        // the compact arrays hold this row's prefix sums at long_off[long_idx]; index them like the full arrays
+        const int ta = tile_ptr[b] - (row_nt[b] > 0 ? (int)long_off[long_idx] : 0);
+        const int ta_real = tile_ptr[b];
         const int64_t slot0 = nslots;
         if (row_nt[b] > 0)
         {
-            const size_t cntt = (size_t)(tb - ta) + 1;
-            h_ob.resize(cntt);
-            h_nc.resize(cntt);
-            h_oc.resize(cntt);
-            h_ws.resize(cntt);
-            TSP_CUDA(cudaMemcpyAsync(h_ob.data(), d_ob.as<long long>() + ta, cntt * sizeof(long long), cudaMemcpyDeviceToHost, s));
-            TSP_CUDA(cudaMemcpyAsync(h_nc.data(), d_nc.as<int>() + ta, cntt * sizeof(int), cudaMemcpyDeviceToHost, s));
-            TSP_CUDA(cudaMemcpyAsync(h_oc.data(), d_oc.as<int>() + ta, cntt * sizeof(int), cudaMemcpyDeviceToHost, s));
-            TSP_CUDA(cudaMemcpyAsync(h_ws.data(), d_ws.as<int>() + ta, cntt * sizeof(int), cudaMemcpyDeviceToHost, s));
-            TSP_CUDA(cudaStreamSynchronize(s));
-            int t = ta;
+            long_idx++;
+            int t = ta_real;
             while (t < tb)
             {
                 // grow the piece [t, te) tile by tile while it still fits
@@ -988,7 +1054,7 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
         {
             // cannot happen (a long row has tiles or side entries); keep y defined anyway
             acc.nrows = 1;
-            items.push_back(PlanItem{b, ta, ta, row_s0[b], row_s0[b], (uint32_t)b, rowlen});
+            items.push_back(PlanItem{b, ta_real, ta_real, row_s0[b], row_s0[b], (uint32_t)b, rowlen});
             close_chunk();
         }
         else
@@ -1506,6 +1572,263 @@ int plan_build(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tiles
     P->b_alg = (nnz_tiled * (2 * vs + 1)) / 2 + 5 * T_tiled + 16 * T_csr + 4 * ((int64_t)dm->tilem + 1) +
                nnz_ext * (vs + 4) + (nnz_ext > 0 ? 4 * (m + 1) : 0) + (int64_t)vs * (n + m);
     P->b_csr = dm->nnz * (vs + 4) + 4 * (m + 1) + (int64_t)vs * (n + m);
+    return TILESPMV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// binary cache of a packed plan (the reference re-converts and re-uploads on every run,
+// tilespmv_cuda.h:794-1056).  File = PlanFileHeader, then per (sub-)plan a PlanRecord followed by its four device
+// buffers (packed stream, chunk descriptors, head lists, split table) as raw bytes; FNV-1a checksum of everything
+// after the header.  A plan is tied to the launch shape it was packed for (the lookahead lists depend on grid x warps),
+// so loading on a GPU with another SM count / shared-memory size is refused and the caller re-plans.
+// ---------------------------------------------------------------------------------------------
+namespace
+{
+struct PlanFileHeader
+{
+    char magic[8]; // "TSPPLAN1"
+    uint32_t version, nplans;
+    int32_t sm_count, smem_optin;
+    uint64_t payload_bytes, checksum;
+};
+struct PlanRecord
+{
+    int32_t precision, rowA, colA, tilem, chunk_bytes, xstage_bytes, head_stride, stage_stride;
+    int32_t grid, block, smem, ctas_per_sm, sm_count, stages, max_warps, flags, format_mask, xpanel_bytes;
+    int32_t accumulate, keep_all_rows, gather_bound, pad0;
+    int64_t nnz, nchunks, stream_bytes, nw, nsplit, nsplit_small, nslots, csr_groups, b_alg, b_csr, xcol_lo, xcol_hi;
+    uint64_t bytes_stream, bytes_desc, bytes_head, bytes_split;
+};
+constexpr uint32_t PLAN_FILE_VERSION = 1;
+
+uint64_t fnv1a(const unsigned char *p, size_t n, uint64_t h)
+{
+    for (size_t i = 0; i < n; i++)
+    {
+        h ^= p[i];
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+
+void fill_record(const tilespmv_plan *P, PlanRecord &r)
+{
+    memset(&r, 0, sizeof(r));
+    r.precision = P->precision;
+    r.rowA = P->rowA;
+    r.colA = P->colA;
+    r.tilem = P->tilem;
+    r.chunk_bytes = P->chunk_bytes;
+    r.xstage_bytes = P->xstage_bytes;
+    r.head_stride = P->head_stride;
+    r.stage_stride = P->stage_stride;
+    r.grid = P->grid;
+    r.block = P->block;
+    r.smem = P->smem;
+    r.ctas_per_sm = P->ctas_per_sm;
+    r.sm_count = P->sm_count;
+    r.stages = P->stages;
+    r.max_warps = P->max_warps;
+    r.flags = P->flags;
+    r.format_mask = P->format_mask;
+    r.xpanel_bytes = P->xpanel_bytes;
+    r.accumulate = P->accumulate;
+    r.keep_all_rows = P->keep_all_rows;
+    r.gather_bound = P->gather_bound;
+    r.nnz = P->nnz;
+    r.nchunks = P->nchunks;
+    r.stream_bytes = P->stream_bytes;
+    r.nw = P->nw;
+    r.nsplit = P->nsplit;
+    r.nsplit_small = P->nsplit_small;
+    r.nslots = P->nslots;
+    r.csr_groups = P->csr_groups;
+    r.b_alg = P->b_alg;
+    r.b_csr = P->b_csr;
+    r.xcol_lo = P->xcol_lo;
+    r.xcol_hi = P->xcol_hi;
+    r.bytes_stream = P->stream.bytes;
+    r.bytes_desc = P->chunk_desc.bytes;
+    r.bytes_head = P->head.bytes;
+    r.bytes_split = (uint64_t)P->nsplit * 4 * sizeof(int);
+}
+} // namespace
+
+int plan_save(const tilespmv_plan *P, const char *path)
+{
+    std::vector<const tilespmv_plan *> all{P};
+    for (const tilespmv_plan *q : P->sub)
+        all.push_back(q);
+    int dev = 0, smem_optin = 0;
+    TSP_CUDA(cudaGetDevice(&dev));
+    TSP_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f)
+    {
+        set_error("plan_save: cannot open %s", tmp.c_str());
+        return TILESPMV_ERR_IO;
+    }
+    PlanFileHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, "TSPPLAN1", 8);
+    h.version = PLAN_FILE_VERSION;
+    h.nplans = (uint32_t)all.size();
+    h.sm_count = P->sm_count;
+    h.smem_optin = smem_optin;
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1; // rewritten at the end with the sizes
+    uint64_t sum = 1469598103934665603ull, payload = 0;
+    std::vector<unsigned char> host;
+    auto put = [&](const void *p, size_t n) {
+        ok = ok && (n == 0 || fwrite(p, 1, n, f) == n);
+        sum = fnv1a(static_cast<const unsigned char *>(p), n, sum);
+        payload += n;
+    };
+    for (const tilespmv_plan *q : all)
+    {
+        PlanRecord r;
+        fill_record(q, r);
+        put(&r, sizeof(r));
+        const std::pair<const DevBuf *, uint64_t> bufs[4] = {{&q->stream, r.bytes_stream}, {&q->chunk_desc, r.bytes_desc},
+                                                             {&q->head, r.bytes_head}, {&q->split_tab, r.bytes_split}};
+        for (const auto &b : bufs)
+        {
+            host.resize((size_t)b.second);
+            if (b.second)
+            {
+                if (cudaMemcpy(host.data(), b.first->p, (size_t)b.second, cudaMemcpyDeviceToHost) != cudaSuccess)
+                {
+                    fclose(f);
+                    remove(tmp.c_str());
+                    set_error("plan_save: D2H failed: %s", cudaGetErrorString(cudaGetLastError()));
+                    return TILESPMV_ERR_CUDA;
+                }
+                put(host.data(), (size_t)b.second);
+            }
+        }
+    }
+    h.payload_bytes = payload;
+    h.checksum = sum;
+    ok = ok && fseek(f, 0, SEEK_SET) == 0 && fwrite(&h, sizeof(h), 1, f) == 1;
+    ok = fclose(f) == 0 && ok;
+    if (!ok || rename(tmp.c_str(), path) != 0)
+    {
+        remove(tmp.c_str());
+        set_error("plan_save: writing %s failed", path);
+        return TILESPMV_ERR_IO;
+    }
+    return TILESPMV_OK;
+}
+
+int plan_load(const char *path, tilespmv_plan **out)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f)
+    {
+        set_error("plan_load: cannot open %s", path);
+        return TILESPMV_ERR_IO;
+    }
+    PlanFileHeader h;
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "TSPPLAN1", 8) != 0 || h.version != PLAN_FILE_VERSION || h.nplans < 1 ||
+        h.nplans > 1024)
+    {
+        fclose(f);
+        set_error("plan_load: %s is not a plan file of this library version", path);
+        return TILESPMV_ERR_IO;
+    }
+    int dev = 0, sms = 0, smem_optin = 0;
+    TSP_CUDA(cudaGetDevice(&dev));
+    TSP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    TSP_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (sms != h.sm_count || smem_optin != h.smem_optin)
+    {
+        fclose(f);
+        set_error("plan_load: %s was planned for %d SMs / %d B of shared memory, this GPU has %d / %d: plan again", path, h.sm_count,
+                  h.smem_optin, sms, smem_optin);
+        return TILESPMV_ERR_UNSUPPORTED;
+    }
+    std::vector<unsigned char> buf((size_t)h.payload_bytes);
+    const bool read_ok = fread(buf.data(), 1, buf.size(), f) == buf.size();
+    fclose(f);
+    if (!read_ok || fnv1a(buf.data(), buf.size(), 1469598103934665603ull) != h.checksum)
+    {
+        set_error("plan_load: %s is truncated or corrupt", path);
+        return TILESPMV_ERR_IO;
+    }
+    tilespmv_plan *root = nullptr;
+    size_t pos = 0;
+    auto fail = [&](int rc) {
+        delete root;
+        return rc;
+    };
+    for (uint32_t k = 0; k < h.nplans; k++)
+    {
+        PlanRecord r;
+        if (pos + sizeof(r) > buf.size())
+            return fail((set_error("plan_load: %s is truncated", path), TILESPMV_ERR_IO));
+        memcpy(&r, buf.data() + pos, sizeof(r));
+        pos += sizeof(r);
+        if (pos + r.bytes_stream + r.bytes_desc + r.bytes_head + r.bytes_split > buf.size())
+            return fail((set_error("plan_load: %s is truncated", path), TILESPMV_ERR_IO));
+        tilespmv_plan *Q = new (std::nothrow) tilespmv_plan();
+        if (!Q)
+            return fail(TILESPMV_ERR_ALLOC);
+        if (k == 0)
+            root = Q;
+        else
+            root->sub.push_back(Q);
+        Q->precision = r.precision;
+        Q->rowA = r.rowA;
+        Q->colA = r.colA;
+        Q->tilem = r.tilem;
+        Q->chunk_bytes = r.chunk_bytes;
+        Q->xstage_bytes = r.xstage_bytes;
+        Q->head_stride = r.head_stride;
+        Q->stage_stride = r.stage_stride;
+        Q->grid = r.grid;
+        Q->block = r.block;
+        Q->smem = r.smem;
+        Q->ctas_per_sm = r.ctas_per_sm;
+        Q->sm_count = r.sm_count;
+        Q->stages = r.stages;
+        Q->max_warps = r.max_warps;
+        Q->flags = r.flags;
+        Q->format_mask = r.format_mask;
+        Q->xpanel_bytes = r.xpanel_bytes;
+        Q->accumulate = r.accumulate != 0;
+        Q->keep_all_rows = r.keep_all_rows != 0;
+        Q->gather_bound = r.gather_bound != 0;
+        Q->nnz = r.nnz;
+        Q->nchunks = r.nchunks;
+        Q->stream_bytes = r.stream_bytes;
+        Q->nw = r.nw;
+        Q->nsplit = r.nsplit;
+        Q->nsplit_small = r.nsplit_small;
+        Q->nslots = r.nslots;
+        Q->csr_groups = r.csr_groups;
+        Q->b_alg = r.b_alg;
+        Q->b_csr = r.b_csr;
+        Q->xcol_lo = r.xcol_lo;
+        Q->xcol_hi = r.xcol_hi;
+        const std::pair<DevBuf *, uint64_t> bufs[4] = {{&Q->stream, r.bytes_stream}, {&Q->chunk_desc, r.bytes_desc}, {&Q->head, r.bytes_head},
+                                                       {&Q->split_tab, r.bytes_split}};
+        for (const auto &b : bufs)
+        {
+            int rc = b.first->alloc((size_t)b.second, false);
+            if (rc != TILESPMV_OK)
+                return fail(rc);
+            if (b.second && cudaMemcpy(b.first->p, buf.data() + pos, (size_t)b.second, cudaMemcpyHostToDevice) != cudaSuccess)
+                return fail((set_error("plan_load: H2D failed: %s", cudaGetErrorString(cudaGetLastError())), TILESPMV_ERR_CUDA));
+            pos += (size_t)b.second;
+        }
+        int rc = Q->scratch.alloc((size_t)Q->nslots * TS * (size_t)Q->precision, true);
+        if (rc == TILESPMV_OK)
+            rc = spmv_set_attrs(Q);
+        if (rc != TILESPMV_OK)
+            return fail(rc);
+    }
+    TSP_CUDA(cudaDeviceSynchronize());
+    *out = root;
     return TILESPMV_OK;
 }
 

@@ -135,4 +135,7 @@ int plan_launch(tilespmv_plan *plan, const void *d_x, void *d_y, cudaStream_t s)
 // fused peer stores ride on the unit flagged `with_peers`
 int plan_launch_unit(tilespmv_plan *plan, int unit, const void *d_x, void *d_y, cudaStream_t s, bool with_peers);
 int spmv_configure(tilespmv_plan *plan); // picks grid / smem, sets the kernel attributes
+int spmv_set_attrs(tilespmv_plan *plan); // kernel attributes only (a plan loaded from a file keeps its launch shape)
+int plan_save(const tilespmv_plan *plan, const char *path);
+int plan_load(const char *path, tilespmv_plan **out);
 } // namespace tsp

@@ -349,9 +349,13 @@ __device__ __forceinline__ void process_chunk(const unsigned char *st, uint32_t 
         const int nsr = (int)(rec.y & 0xffffu);
         const int nother = (int)(rec.y >> 16);
         const bool has_side = (rec.z & (ROWF_HAS_SIDE << 8)) != 0;
-        uint32_t wt = 0;
+        uint32_t w0 = 0, w1 = 0, wt = 0;
         if (has_side) // issued early: independent of the ELL loop
-            wt = lds_u32(sidehdr_s + 32u - 4u * (uint32_t)p); // total | long-row mask << 16
+        {
+            w0 = lds_u32(sidehdr_s);
+            w1 = lds_u32(sidehdr_s + 4u);
+            wt = lds_u32(sidehdr_s + 32u - 4u * (uint32_t)p);
+        }
         T a0 = 0, a1 = 0;
 
         // ---- ELL group: one flat loop over the slot-rows of all ELL tiles of the row, 4 slot-rows
@@ -604,56 +608,41 @@ __device__ __forceinline__ void process_chunk(const unsigned char *st, uint32_t 
             }
         }
 
-        // ---- extracted very-sparse nonzeros of this block row: 4 lanes per row pair, one predicated loop with a
-        //      warp-uniform trip count.  Here lane (g, p) works on local rows p and p + 8 (NOT 2p / 2p + 1): with rows of
-        //      equal length L the 8 row pairs then start L entries apart instead of 2L, and for L = 20 (uniform random,
-        //      config 5) the 32 lanes of a load hit every shared-memory bank exactly twice, where the 2L spacing put four
-        //      row pairs on the same banks (4-way conflicts on both the value and the staged-x loads: 37 % of all
-        //      shared-memory wavefronts of the uniform 1 M x 20 capture).  The two sums are handed to the lanes that own
-        //      rows 2p / 2p + 1 with four shuffles per block row. ----
+        // ---- extracted very-sparse nonzeros of this block row: 4 lanes per row pair, one
+        //      predicated loop with a warp-uniform trip count, 4 trips' loads in flight at once ----
         pay_s = st_s + (uint32_t)(pay - st);
         if (has_side)
         {
-            const uint32_t hdr0_s = sidehdr_s - 4u * (uint32_t)p; // the 17 row starts + long-row mask of this block row
-            const uint32_t s0 = lds_u16(hdr0_s + 2u * (uint32_t)p), e0 = lds_u16(hdr0_s + 2u * (uint32_t)p + 2u);
-            const uint32_t s1 = lds_u16(hdr0_s + 2u * (uint32_t)p + 16u), e1 = lds_u16(hdr0_s + 2u * (uint32_t)p + 18u);
-            uint32_t k0 = s0 + (uint32_t)g, k1 = s1 + (uint32_t)g;
+            const uint32_t s1 = w0 >> 16, e1 = w1 & 0xffffu;
+            uint32_t k0 = (w0 & 0xffffu) + (uint32_t)g, k1 = s1 + (uint32_t)g;
             const int nit = (int)(rec.z >> 16);
             // rows with many entries (pieces of hub rows of power-law matrices) would keep 4 lanes busy for hundreds
             // of trips: the whole warp sums them instead (below), this loop skips them
             const uint32_t longmask = wt >> 16;
             if (longmask)
             {
-                if ((longmask >> p) & 1u)
-                    k0 = e0;
-                if ((longmask >> (p + 8)) & 1u)
+                if ((longmask >> (2 * p)) & 1u)
+                    k0 = s1;
+                if ((longmask >> (2 * p + 1)) & 1u)
                     k1 = e1;
             }
-            T b0 = 0, b1 = 0;
 #pragma unroll 1
             for (int i = 0; i < nit; i += 2) // trips past a lane's last entry are predicated off
             {
-                if (k0 < e0)
-                    b0 = fma_t<T>(sideval[k0], xside[k0], b0);
+                if (k0 < s1)
+                    a0 = fma_t<T>(sideval[k0], xside[k0], a0);
                 if (k1 < e1)
-                    b1 = fma_t<T>(sideval[k1], xside[k1], b1);
-                if (k0 + 4u < e0)
-                    b0 = fma_t<T>(sideval[k0 + 4u], xside[k0 + 4u], b0);
+                    a1 = fma_t<T>(sideval[k1], xside[k1], a1);
+                if (k0 + 4u < s1)
+                    a0 = fma_t<T>(sideval[k0 + 4u], xside[k0 + 4u], a0);
                 if (k1 + 4u < e1)
-                    b1 = fma_t<T>(sideval[k1 + 4u], xside[k1 + 4u], b1);
+                    a1 = fma_t<T>(sideval[k1 + 4u], xside[k1 + 4u], a1);
                 k0 += 8u;
                 k1 += 8u;
             }
-            {
-                // row r lives in lane (g, r & 7) as b0 (r < 8) or b1; lane (g, p) wants rows 2p and 2p + 1
-                const int src0 = (lane & 24) | ((2 * p) & 7), src1 = (lane & 24) | ((2 * p + 1) & 7);
-                const T u0 = __shfl_sync(0xffffffffu, b0, src0), u1 = __shfl_sync(0xffffffffu, b1, src0);
-                const T v0 = __shfl_sync(0xffffffffu, b0, src1), v1 = __shfl_sync(0xffffffffu, b1, src1);
-                a0 += p < 4 ? u0 : u1;
-                a1 += p < 4 ? v0 : v1;
-            }
             if (longmask) // warp-uniform
             {
+                const uint32_t hdr0_s = sidehdr_s - 4u * (uint32_t)p;
                 uint32_t lm = longmask;
 #pragma unroll 1
                 while (lm)
@@ -984,6 +973,21 @@ int spmv_configure(tilespmv_plan *P)
     else
         TSP_TRY(set_kernel_attrs<float>(P->stages, warps, smem_optin));
     return TILESPMV_OK;
+}
+
+int spmv_set_attrs(tilespmv_plan *P)
+{
+    int dev = 0, smem_optin = 0;
+    TSP_CUDA(cudaGetDevice(&dev));
+    TSP_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (P->smem > smem_optin || P->block < 32 || P->block > 1024 || P->stages < 2 || P->stages > SPMV_MAX_STAGES)
+    {
+        set_error("plan: launch shape (%d threads, %d B of shared memory, %d stages) does not fit this GPU", P->block, P->smem, P->stages);
+        return TILESPMV_ERR_UNSUPPORTED;
+    }
+    if (P->precision == 8)
+        return set_kernel_attrs<double>(P->stages, P->block / 32, smem_optin);
+    return set_kernel_attrs<float>(P->stages, P->block / 32, smem_optin);
 }
 
 template <class T>
