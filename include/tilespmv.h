@@ -252,6 +252,9 @@ typedef struct
 /* keep every CSR tile an individual tile of the packed stream instead of merging the CSR tiles of a block row
  * into one jagged slot-row list (the default, faster; results agree to rounding) */
 #define TILESPMV_PLAN_NO_CSR_GROUPS 1
+/* pack chunks that hold only extracted (side) entries like every other chunk instead of in the flat jagged-diagonal
+ * layout (the default for them, several times fewer instructions per row; results agree to rounding) */
+#define TILESPMV_PLAN_NO_FLAT_SIDE 2
 
 /* Packs the tiles into the 16-byte-aligned per-chunk stream and builds the persistent,
  * byte-balanced chunk schedule.  opts may be NULL. */

@@ -17,6 +17,7 @@ F64, F32 = 8, 4
 CSR_ON_DEVICE = 1
 ENABLE_HYB = 2
 PLAN_NO_CSR_GROUPS = 1
+PLAN_NO_FLAT_SIDE = 2
 OK = 0
 ERR_NODEVICE = -5
 

@@ -176,10 +176,10 @@ class Plan:
     """tilespmv_plan: packed stream + persistent chunk schedule for one DeviceTileMatrix."""
 
     def __init__(self, dmat, chunk_bytes=0, xstage_bytes=0, ctas_per_sm=0, stages=0, max_warps=0, csr_groups=True,
-                 xpanel_bytes=0, format_mask=0):
+                 xpanel_bytes=0, format_mask=0, flat_side=True):
         L = _capi.load()
-        opts = _capi.PlanOptions(chunk_bytes, xstage_bytes, ctas_per_sm, stages, max_warps,
-                                 0 if csr_groups else _capi.PLAN_NO_CSR_GROUPS, xpanel_bytes, format_mask)
+        flags = (0 if csr_groups else _capi.PLAN_NO_CSR_GROUPS) | (0 if flat_side else _capi.PLAN_NO_FLAT_SIDE)
+        opts = _capi.PlanOptions(chunk_bytes, xstage_bytes, ctas_per_sm, stages, max_warps, flags, xpanel_bytes, format_mask)
         h = C.c_void_p()
         check(L.tilespmv_plan_create(dmat.handle, C.byref(opts), C.byref(h)), "tilespmv_plan_create")
         self.handle, self.precision = h, dmat.precision

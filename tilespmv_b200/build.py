@@ -32,7 +32,9 @@ LINK_LIBS = ["-lcudart", "-lnccl", "-lgomp", "-lrt", "-lpthread"]
 def _digest(sources, flags):
     """Content hash of the sources + the command line (mtimes do not survive a snapshot copy to the GPU box)."""
     import hashlib
-    h = hashlib.sha256(" ".join(flags).encode())
+    # absolute paths inside the flags (-I<repo>/include ...) must not enter the digest: the GPU box unpacks the repo
+    # somewhere else, and a digest that changes with the location makes EVERY process there rebuild the library
+    h = hashlib.sha256(" ".join(f.replace(ROOT, "<repo>") for f in flags).encode())
     for s in sorted(sources):
         h.update(os.path.basename(s).encode())
         with open(s, "rb") as f:
@@ -85,6 +87,19 @@ def build_cuda(force=False, verbose=False, extra=()):
     flags = NVCC_FLAGS + list(extra) + LINK_LIBS
     if not (force or _stale(LIB_CUDA, cuda_deps(), flags)):
         return LIB_CUDA
+    # one builder at a time (the ranks of a torchrun job all come through here): take the lock, then look again
+    import fcntl
+    with open(os.path.join(PKG, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not (force or _stale(LIB_CUDA, cuda_deps(), flags)):
+                return LIB_CUDA
+            return _build_cuda_locked(force, verbose, extra, flags)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_cuda_locked(force, verbose, extra, flags):
     from concurrent.futures import ThreadPoolExecutor
     objdir = os.path.join(PKG, "build")
     os.makedirs(objdir, exist_ok=True)
@@ -103,10 +118,12 @@ def build_cuda(force=False, verbose=False, extra=()):
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, cuda_sources()))
-    cmd = [NVCC, "-shared", "-ccbin", GPP] + objs + ["-o", LIB_CUDA] + LINK_LIBS
+    tmp = LIB_CUDA + ".tmp%d" % os.getpid()
+    cmd = [NVCC, "-shared", "-ccbin", GPP] + objs + ["-o", tmp] + LINK_LIBS
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
+    os.replace(tmp, LIB_CUDA)  # atomic: a concurrent reader never maps a half-written library
     _stamp(LIB_CUDA, cuda_deps(), flags)
     return LIB_CUDA
 

@@ -42,7 +42,7 @@ namespace tsp
 constexpr uint32_t SHM_MAGIC = 0x43505354u; // "TSPC"
 constexpr int COMM_MAX_RANKS = 16;
 constexpr size_t DIST_FLAG_BYTES = 1024; // D[16] | A[16] | error word, then the two x buffers
-constexpr size_t DIST_OFF_D = 0, DIST_OFF_A = 64, DIST_OFF_ERR = 128;
+constexpr size_t DIST_OFF_D = 0, DIST_OFF_A = 64, DIST_OFF_ERR = 128, DIST_OFF_EPOCH = 192;
 
 struct ShmSlot
 {
@@ -92,7 +92,17 @@ struct tilespmv_dist
     unsigned char *peer_block[tsp::COMM_MAX_RANKS] = {nullptr};
     bool peer_mapped[tsp::COMM_MAX_RANKS] = {false};
     int peer_device[tsp::COMM_MAX_RANKS] = {0};
-    cudaStream_t s_comm = nullptr;
+    cudaStream_t s_comm = nullptr, s_main = nullptr; // copy stream / the stream the loop itself runs on
+    cudaEvent_t ev_user = nullptr, ev_done = nullptr; // hand-over between the caller's stream and s_main
+    // the enqueued work of one call (all iterations, both streams) captured into a CUDA graph, keyed by its shape
+    struct GraphEntry
+    {
+        int exchange, niters, cur;
+        cudaGraphExec_t exec;
+        int64_t launches;
+    };
+    std::vector<GraphEntry> graphs;
+    bool use_graph = true;
     cudaEvent_t ev_kernel[2] = {nullptr, nullptr}, ev_push[2] = {nullptr, nullptr};
     bool ev_push_valid[2] = {false, false};
     uint32_t epoch = 1; // next unused epoch (flags start at 0)
@@ -114,11 +124,14 @@ struct tilespmv_dist
         for (int r = 0; r < tsp::COMM_MAX_RANKS; r++)
             if (peer_mapped[r])
                 cudaIpcCloseMemHandle(peer_block[r]);
-        for (cudaEvent_t e : {ev_kernel[0], ev_kernel[1], ev_push[0], ev_push[1]})
+        for (GraphEntry &g : graphs)
+            cudaGraphExecDestroy(g.exec);
+        for (cudaEvent_t e : {ev_kernel[0], ev_kernel[1], ev_push[0], ev_push[1], ev_user, ev_done})
             if (e)
                 cudaEventDestroy(e);
-        if (s_comm)
-            cudaStreamDestroy(s_comm);
+        for (cudaStream_t st : {s_comm, s_main})
+            if (st)
+                cudaStreamDestroy(st);
         delete plan;
     }
 };
@@ -332,28 +345,36 @@ struct SignalArgs
 {
     uint32_t *ptr[COMM_MAX_RANKS];
     int n;
-    uint32_t value;
+    uint32_t delta;
+    const uint32_t *base;
 };
 
-// thread i stores `value` into remote (or local) flag ptr[i]; everything the stream did before is visible first
+// All flag values are RELATIVE to the epoch of the running call, which lives in a device word (set once per call):
+// the kernels below take (base pointer, delta).  The enqueued work of a call therefore does not depend on the absolute
+// epoch and can be captured into a CUDA graph once and replayed for every later call of the same shape.
+__global__ void __launch_bounds__(32) set_epoch_kernel(uint32_t *word, uint32_t value) { *word = value; }
+
+// thread i stores *base + delta into remote (or local) flag ptr[i]; everything the stream did before is visible first
 __global__ void __launch_bounds__(32) flag_signal_kernel(SignalArgs a)
 {
     const int i = (int)threadIdx.x;
     if (i < a.n)
     {
+        const uint32_t value = *a.base + a.delta;
         __threadfence_system();
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.ptr[i]), "r"(a.value) : "memory");
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.ptr[i]), "r"(value) : "memory");
     }
 }
 
-// thread i (for every bit i of mask) spins until flags[i] >= target (wrap-safe); gives up after timeout_ns and
+// thread i (for every bit i of mask) spins until flags[i] >= *base + delta (wrap-safe); gives up after timeout_ns and
 // records 1 + i in *err so that a dead peer becomes an error instead of a hung GPU
 __global__ void __launch_bounds__(32)
-    flag_wait_kernel(const uint32_t *flags, uint32_t mask, uint32_t target, uint32_t *err, unsigned long long timeout_ns)
+    flag_wait_kernel(const uint32_t *flags, uint32_t mask, const uint32_t *base, uint32_t delta, uint32_t *err, unsigned long long timeout_ns)
 {
     const int i = (int)threadIdx.x;
     if (!((mask >> i) & 1u))
         return;
+    const uint32_t target = *base + delta;
     unsigned long long t0 = 0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     unsigned spins = 0;
@@ -377,22 +398,24 @@ __global__ void __launch_bounds__(32)
     }
 }
 
-static int flag_wait(tilespmv_dist *d, size_t off, uint32_t mask, uint32_t target, cudaStream_t s)
+// wait until flags[off][r] >= (epoch of the call) + delta for every rank r of mask
+static int flag_wait(tilespmv_dist *d, size_t off, uint32_t mask, uint32_t delta, cudaStream_t s)
 {
     if (!mask)
         return TILESPMV_OK;
     unsigned char *b = d->block.as<unsigned char>();
-    TSP_LAUNCH(flag_wait_kernel, 1, 32, 0, s, reinterpret_cast<const uint32_t *>(b + off), mask, target,
-               reinterpret_cast<uint32_t *>(b + DIST_OFF_ERR), d->spin_timeout_ns);
+    TSP_LAUNCH(flag_wait_kernel, 1, 32, 0, s, reinterpret_cast<const uint32_t *>(b + off), mask, reinterpret_cast<const uint32_t *>(b + DIST_OFF_EPOCH),
+               delta, reinterpret_cast<uint32_t *>(b + DIST_OFF_ERR), d->spin_timeout_ns);
     return TILESPMV_OK;
 }
 
-// store `value` into flag row `off`, entry `d->rank`, on every rank of mask
-static int flag_signal(tilespmv_dist *d, size_t off, uint32_t mask, uint32_t value, cudaStream_t s)
+// store (epoch of the call) + delta into flag row `off`, entry `d->rank`, on every rank of mask
+static int flag_signal(tilespmv_dist *d, size_t off, uint32_t mask, uint32_t delta, cudaStream_t s)
 {
     SignalArgs a;
     a.n = 0;
-    a.value = value;
+    a.delta = delta;
+    a.base = reinterpret_cast<const uint32_t *>(d->block.as<unsigned char>() + DIST_OFF_EPOCH);
     for (int r = 0; r < d->nranks; r++)
         if ((mask >> r) & 1u)
             a.ptr[a.n++] = reinterpret_cast<uint32_t *>(d->peer_block[r] + off) + d->rank;
@@ -611,12 +634,17 @@ static int dist_create(tilespmv_comm *c, const tilespmv_dmat *dm, const int64_t 
         cudaEventCreate(&d->dbg0);
         cudaEventCreate(&d->dbg1);
     }
-    if (cudaStreamCreateWithFlags(&d->s_comm, cudaStreamNonBlocking) != cudaSuccess)
+    if (const char *e = getenv("TILESPMV_DIST_NO_GRAPH"))
+        d->use_graph = atoi(e) == 0;
+    if (d->debug)
+        d->use_graph = false; // the push timing events cannot be read back from a graph
+    if (cudaStreamCreateWithFlags(&d->s_main, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&d->s_comm, cudaStreamNonBlocking) != cudaSuccess)
     {
         set_error("dist_create: cudaStreamCreate failed");
         return fail(TILESPMV_ERR_CUDA);
     }
-    for (cudaEvent_t *e : {&d->ev_kernel[0], &d->ev_kernel[1], &d->ev_push[0], &d->ev_push[1]})
+    for (cudaEvent_t *e : {&d->ev_kernel[0], &d->ev_kernel[1], &d->ev_push[0], &d->ev_push[1], &d->ev_user, &d->ev_done})
         if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess)
         {
             set_error("dist_create: cudaEventCreate failed");
@@ -666,13 +694,12 @@ static int iterate_nccl(tilespmv_dist *d, int niters, cudaStream_t s)
             TSP_NCCL(ncclGroupEnd());
         }
     }
-    d->cur = (d->cur + niters) & 1;
     return TILESPMV_OK;
 }
 
 static int iterate_fused(tilespmv_dist *d, int niters, cudaStream_t s)
 {
-    const uint32_t peers = all_peers_mask(d), E0 = d->epoch;
+    const uint32_t peers = all_peers_mask(d), E0 = 0; // flag values are deltas to the call's epoch
     TSP_TRY(flag_signal(d, DIST_OFF_A, peers, E0, s)); // entered the call: my buffers are free for epoch E0
     for (int i = 0; i < niters; i++)
     {
@@ -692,14 +719,12 @@ static int iterate_fused(tilespmv_dist *d, int niters, cudaStream_t s)
     }
     TSP_TRY(flag_wait(d, DIST_OFF_A, peers, E0 + (uint32_t)niters, s)); // the final x is complete on this rank
     tilespmv_plan_set_peers(d->plan, 0, nullptr, 0);
-    d->epoch = E0 + (uint32_t)niters + 1;
-    d->cur = (d->cur + niters) & 1;
     return TILESPMV_OK;
 }
 
 static int iterate_pipelined(tilespmv_dist *d, int niters, cudaStream_t s)
 {
-    const uint32_t peers = all_peers_mask(d), E0 = d->epoch;
+    const uint32_t peers = all_peers_mask(d), E0 = 0; // flag values are deltas to the call's epoch
     const int R = d->nranks, me = d->rank, nunits = 1 + (int)d->plan->sub.size();
     const size_t slice_off = (size_t)d->r0 * (size_t)d->vs, slice_bytes = (size_t)d->m_local * (size_t)d->vs;
     d->ev_push_valid[0] = d->ev_push_valid[1] = false;
@@ -754,8 +779,6 @@ static int iterate_pipelined(tilespmv_dist *d, int niters, cudaStream_t s)
     for (int b = 0; b < 2; b++)
         if (d->ev_push_valid[b])
             TSP_CUDA(cudaStreamWaitEvent(s, d->ev_push[b], 0));
-    d->epoch = E0 + (uint32_t)niters + 1;
-    d->cur = (d->cur + niters) & 1;
     return TILESPMV_OK;
 }
 
@@ -767,7 +790,7 @@ static int iterate_halo(tilespmv_dist *d, int niters, cudaStream_t s)
 {
     if (!d->halo_ok)
         return iterate_pipelined(d, niters, s);
-    const uint32_t peers = all_peers_mask(d), E0 = d->epoch;
+    const uint32_t peers = all_peers_mask(d), E0 = 0; // flag values are deltas to the call's epoch
     const int R = d->nranks, me = d->rank;
     const size_t vs = (size_t)d->vs, slice_off = (size_t)d->r0 * vs;
     d->ev_push_valid[0] = d->ev_push_valid[1] = false;
@@ -836,8 +859,6 @@ static int iterate_halo(tilespmv_dist *d, int niters, cudaStream_t s)
         if (d->ev_push_valid[b])
             TSP_CUDA(cudaStreamWaitEvent(s, d->ev_push[b], 0));
     tilespmv_plan_set_peers(d->plan, 0, nullptr, 0);
-    d->epoch = E0 + (uint32_t)niters + 1;
-    d->cur = (d->cur + niters) & 1;
     return TILESPMV_OK;
 }
 
@@ -886,32 +907,108 @@ void tilespmv_dist_destroy(tilespmv_dist *dist)
     delete dist;
 }
 
+// enqueue all iterations of one call on s_main (+ s_comm)
+static int iterate_enqueue(tilespmv_dist *d, int niters, int exchange)
+{
+    switch (exchange)
+    {
+    case TILESPMV_EXCHANGE_FUSED:
+        return iterate_fused(d, niters, d->s_main);
+    case TILESPMV_EXCHANGE_PIPELINED:
+        return iterate_pipelined(d, niters, d->s_main);
+    case TILESPMV_EXCHANGE_HALO:
+        return iterate_halo(d, niters, d->s_main);
+    default:
+        return iterate_nccl(d, niters, d->s_main);
+    }
+}
+
 int tilespmv_dist_iterate(tilespmv_dist *dist, const void *d_x0, int niters, int exchange, void *stream)
 {
     clear_error();
-    if (!dist || niters < 0)
+    if (!dist || niters < 0 || exchange < TILESPMV_EXCHANGE_NCCL || exchange > TILESPMV_EXCHANGE_HALO)
     {
         set_error("dist_iterate: invalid argument");
         return TILESPMV_ERR_INVALID;
     }
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    tilespmv_dist *d = dist;
+    cudaStream_t su = static_cast<cudaStream_t>(stream);
     if (d_x0)
     {
-        dist->cur = 0;
-        TSP_CUDA(cudaMemcpyAsync(xbuf(dist, dist->rank, 0), d_x0, (size_t)dist->n * (size_t)dist->vs, cudaMemcpyDeviceToDevice, s));
+        d->cur = 0;
+        TSP_CUDA(cudaMemcpyAsync(xbuf(d, d->rank, 0), d_x0, (size_t)d->n * (size_t)d->vs, cudaMemcpyDeviceToDevice, su));
     }
     if (niters == 0)
         return TILESPMV_OK;
-    if (dist->nranks == 1 || exchange == TILESPMV_EXCHANGE_NCCL)
-        return iterate_nccl(dist, niters, s);
-    if (exchange == TILESPMV_EXCHANGE_FUSED)
-        return iterate_fused(dist, niters, s);
-    if (exchange == TILESPMV_EXCHANGE_PIPELINED)
-        return iterate_pipelined(dist, niters, s);
-    if (exchange == TILESPMV_EXCHANGE_HALO)
-        return iterate_halo(dist, niters, s);
-    set_error("dist_iterate: unknown exchange %d", exchange);
-    return TILESPMV_ERR_INVALID;
+    if (d->nranks == 1)
+        exchange = TILESPMV_EXCHANGE_NCCL; // nothing to exchange: plain ping-pong
+    // the loop runs on the library's own stream (the caller's may be the legacy default stream, which cannot be captured)
+    TSP_CUDA(cudaEventRecord(d->ev_user, su));
+    TSP_CUDA(cudaStreamWaitEvent(d->s_main, d->ev_user, 0));
+    TSP_LAUNCH(set_epoch_kernel, 1, 1, 0, d->s_main, reinterpret_cast<uint32_t *>(d->block.as<unsigned char>() + DIST_OFF_EPOCH), d->epoch);
+    int rc = TILESPMV_OK;
+    const bool graphable = d->use_graph && exchange != TILESPMV_EXCHANGE_NCCL;
+    if (graphable)
+    {
+        tilespmv_dist::GraphEntry *g = nullptr;
+        for (auto &e : d->graphs)
+            if (e.exchange == exchange && e.niters == niters && e.cur == d->cur)
+                g = &e;
+        if (!g)
+        {
+            const int64_t counted = g_launches.load();
+            cudaGraph_t graph = nullptr;
+            cudaError_t ce = cudaStreamBeginCapture(d->s_main, cudaStreamCaptureModeThreadLocal);
+            if (ce == cudaSuccess)
+            {
+                rc = iterate_enqueue(d, niters, exchange);
+                ce = cudaStreamEndCapture(d->s_main, &graph);
+            }
+            const int64_t captured = g_launches.load() - counted;
+            g_launches.store(counted); // launches recorded while capturing are not executions
+            cudaGraphExec_t exec = nullptr;
+            if (rc == TILESPMV_OK && ce == cudaSuccess && graph)
+                ce = cudaGraphInstantiate(&exec, graph, 0);
+            if (graph)
+                cudaGraphDestroy(graph);
+            if (rc != TILESPMV_OK || ce != cudaSuccess || !exec)
+            {
+                // e.g. a driver that cannot capture peer copies: enqueue directly from now on (a real error shows up again there)
+                cudaGetLastError();
+                if (exec)
+                    cudaGraphExecDestroy(exec);
+                d->use_graph = false;
+                rc = TILESPMV_OK;
+                clear_error();
+            }
+            else
+            {
+                if (d->graphs.size() >= 8)
+                {
+                    cudaGraphExecDestroy(d->graphs.front().exec);
+                    d->graphs.erase(d->graphs.begin());
+                }
+                d->graphs.push_back({exchange, niters, d->cur, exec, captured});
+                g = &d->graphs.back();
+            }
+        }
+        if (g)
+        {
+            TSP_CUDA(cudaGraphLaunch(g->exec, d->s_main));
+            g_launches.fetch_add(g->launches, std::memory_order_relaxed);
+        }
+        else
+            rc = iterate_enqueue(d, niters, exchange);
+    }
+    else
+        rc = iterate_enqueue(d, niters, exchange);
+    TSP_TRY(rc);
+    if (exchange != TILESPMV_EXCHANGE_NCCL)
+        d->epoch += (uint32_t)niters + 1u;
+    d->cur = (d->cur + niters) & 1;
+    TSP_CUDA(cudaEventRecord(d->ev_done, d->s_main));
+    TSP_CUDA(cudaStreamWaitEvent(su, d->ev_done, 0));
+    return TILESPMV_OK;
 }
 
 void *tilespmv_dist_x(tilespmv_dist *dist)
@@ -935,6 +1032,7 @@ int tilespmv_dist_sync(tilespmv_dist *dist, void *stream)
         return TILESPMV_ERR_INVALID;
     }
     TSP_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    TSP_CUDA(cudaStreamSynchronize(dist->s_main));
     TSP_CUDA(cudaStreamSynchronize(dist->s_comm));
     if (dist->dbg_armed)
     {

@@ -196,6 +196,7 @@ struct PackArgs
     int stages;          // TMA pipeline depth the stream is laid out for
     int head_stride;
     int side_long_row;   // local rows with at least this many side entries are summed by the whole warp
+    int allow_flat;      // side-only chunks are packed in the flat layout (stream.cuh)
     int *error_flag;
     // Tile_matrix (device)
     int rowA, colA, tilem, tilen;
@@ -420,6 +421,80 @@ __device__ void pack_csr_group(const PackArgs<T> &a, const PlanItem &it, unsigne
     }
 }
 
+// Order of the extracted nonzeros inside a FLAT chunk (stream.cuh): 32 local rows per round, inside a round slot-major
+// without padding, rows with >= FLAT_LONG_ROW entries after all rounds in row order.  Runs on ONE warp; calls
+// f(position in the chunk, index into the side arrays) for every entry, fills len[] / FlatLong[] when given.  The SpMV
+// kernel (process_chunk_flat) walks the rounds with the same ballot / popc arithmetic.
+template <class T, class F>
+__device__ void flat_walk(const PackArgs<T> &a, long long c, int lane, F f, unsigned char *lens, FlatLong *longtab, int *nlong_out)
+{
+    const long long j0 = a.chunk_item0[c];
+    const int nrows16 = (int)(a.chunk_item0[c + 1] - j0) * TS;
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t pos = 0;
+    int nlong = 0;
+    for (int pass = 0; pass < 2; pass++)
+        for (int rd = 0; rd * 32 < nrows16; rd++)
+        {
+            const int rho = rd * 32 + lane;
+            int len = 0, src = 0;
+            if (rho < nrows16)
+            {
+                const PlanItem it = a.items[j0 + (rho >> 4)];
+                const int r = rho & 15;
+                if (r < it.rowlen)
+                {
+                    int lo = a.side_ptr[it.br * TS + r], hi = a.side_ptr[it.br * TS + r + 1];
+                    lo = min(max(lo, it.s0), it.s1);
+                    hi = min(max(hi, it.s0), it.s1);
+                    len = hi - lo;
+                    src = lo;
+                }
+            }
+            const bool is_long = len >= FLAT_LONG_ROW;
+            if (pass == 0)
+            {
+                if (lens && rho < nrows16)
+                    lens[rho] = (unsigned char)(is_long ? 0 : len);
+                const int jl = is_long ? 0 : len;
+                for (int j = 0;; j++)
+                {
+                    const unsigned mask = __ballot_sync(0xffffffffu, jl > j);
+                    if (!mask)
+                        break;
+                    if (jl > j)
+                        f(pos + (uint32_t)__popc(mask & lt), src + j);
+                    pos += (uint32_t)__popc(mask);
+                }
+            }
+            else
+            {
+                unsigned lm = __ballot_sync(0xffffffffu, is_long);
+                while (lm)
+                {
+                    const int l = __ffs((int)lm) - 1;
+                    lm &= lm - 1u;
+                    const int L = __shfl_sync(0xffffffffu, len, l), S = __shfl_sync(0xffffffffu, src, l);
+                    for (int q = lane; q < L; q += 32)
+                        f(pos + (uint32_t)q, S + q);
+                    if (lane == 0 && longtab)
+                    {
+                        FlatLong fl;
+                        fl.row = (uint16_t)(rd * 32 + l);
+                        fl.start = (uint16_t)pos;
+                        fl.count = (uint16_t)L;
+                        fl.pad = 0;
+                        longtab[nlong] = fl;
+                    }
+                    nlong++;
+                    pos += (uint32_t)L;
+                }
+            }
+        }
+    if (nlong_out)
+        *nlong_out = nlong;
+}
+
 constexpr int PACK_ITEM_INTS = 6; // per item: tile base, other base, payload base, side base, sidehdr idx, nsr
 
 // x-staging lists of chunk cn (tile column of every stream tile, global column of every extracted
@@ -432,6 +507,19 @@ __device__ unsigned write_lists(const PackArgs<T> &a, long long cn, uint32_t *ti
     const bool ragged_cols = (a.colA % TS) != 0;
     unsigned flags = 0;
     int tbase = 0, sbase = 0;
+    if (a.allow_flat)
+    {
+        // a chunk without stream tiles is flat: its side columns go in the flat order (warp 0 walks it)
+        bool any_tile = false;
+        for (long long j = j0; j < j1 && !any_tile; j++)
+            any_tile = a.sc.nc[a.items[j].t1] != a.sc.nc[a.items[j].t0];
+        if (!any_tile)
+        {
+            if (threadIdx.x < 32)
+                flat_walk<T>(a, cn, (int)threadIdx.x, [&](uint32_t pos, int src) { sidecol[pos] = (uint32_t)a.side_col[src]; }, nullptr, nullptr, nullptr);
+            return 0u;
+        }
+    }
     for (long long j = j0; j < j1; j++)
     {
         const PlanItem it = a.items[j];
@@ -475,6 +563,7 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long 
     __shared__ int s_start[TS + 1];
     __shared__ unsigned s_flags, s_head_flags;
     __shared__ uint32_t s_own_nt, s_own_ns;
+    __shared__ int s_flat;
     __shared__ int g_start[TS][CSRGROUP_MAX_TILES], g_len[TS];
     __shared__ unsigned g_hdr[CSRGROUP_MAX_SLOTROWS];
     const long long c = blockIdx.x;
@@ -529,11 +618,24 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long 
         hdr.ntiles = (uint16_t)ntiles;
         hdr.next_ntiles = (uint16_t)next_nt;
         hdr.next_nside = (uint16_t)next_ns;
-        const uint32_t off_odesc = CHUNK_OFF_ROWS + 16u * (uint32_t)nitems;
-        const uint32_t off_sidehdr = off_odesc + pad16(8u * nother);
-        const uint32_t off_sideval = off_sidehdr + pad16(SIDEHDR_BYTES * nsiderows);
-        const uint32_t off_payload = off_sideval + pad16(vs * nside);
-        const uint32_t off_nextlist = off_payload + pay;
+        const bool flat = a.allow_flat && ntiles == 0; // no stream tile in the chunk: flat layout (stream.cuh)
+        uint32_t off_odesc = CHUNK_OFF_ROWS + 16u * (uint32_t)nitems;
+        uint32_t off_sidehdr = off_odesc + pad16(8u * nother);
+        uint32_t off_sideval = off_sidehdr + pad16(SIDEHDR_BYTES * nsiderows);
+        uint32_t off_payload = off_sideval + pad16(vs * nside);
+        uint32_t off_nextlist = off_payload + pay;
+        if (flat)
+        {
+            off_sidehdr = CHUNK_OFF_ROWS + 16u * (uint32_t)nitems;                       // len[16 nrows]
+            off_payload = off_sidehdr + 16u * (uint32_t)nitems;                          // FlatLong[]
+            off_sideval = off_payload + pad16(8u * (nside / (uint32_t)FLAT_LONG_ROW));   // val[nside]
+            off_nextlist = off_sideval + pad16(vs * nside);
+            off_odesc = 0;                                                               // number of FlatLong records, set by the walk
+            hdr.nrows = (uint16_t)((uint32_t)nitems | CHF_FLAT);
+            if (nitems > FLAT_MAX_ROWS)
+                atomicExch(a.error_flag, 1);
+        }
+        s_flat = flat ? 1 : 0;
         hdr.off_nextlist = (uint16_t)off_nextlist;
         hdr.off_odesc = (uint16_t)off_odesc;
         hdr.off_sidehdr = (uint16_t)off_sidehdr;
@@ -557,7 +659,23 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(PackArgs<T> a, long 
     }
     __syncthreads();
 
-    for (int k = 0; k < nitems; k++)
+    if (s_flat) // uniform across the CTA: values in the flat order, len[] and the long-row table (one warp walks the chunk)
+    {
+        if (threadIdx.x < 32)
+        {
+            T *ov = reinterpret_cast<T *>(out + hdr.off_sideval);
+            int nlong = 0;
+            flat_walk<T>(a, c, (int)threadIdx.x, [&](uint32_t pos, int src) { ov[pos] = a.side_val[src]; }, out + hdr.off_sidehdr,
+                         reinterpret_cast<FlatLong *>(out + hdr.off_payload), &nlong);
+            if (threadIdx.x == 0)
+            {
+                reinterpret_cast<ChunkHeader *>(out)->off_odesc = (uint16_t)nlong;
+                if ((uint32_t)nlong > hdr.nside / (uint32_t)FLAT_LONG_ROW)
+                    atomicExch(a.error_flag, 1);
+            }
+        }
+    }
+    for (int k = 0; k < (s_flat ? 0 : nitems); k++)
     {
         const PlanItem it = a.items[i0 + k];
         const int *sb = s_base + PACK_ITEM_INTS * k;
@@ -677,14 +795,20 @@ namespace
 struct ChunkAcc
 {
     uint32_t nrows = 0, ntiles = 0, nother = 0, nsiderows = 0, nside = 0, payload = 0;
+    bool allow_flat = false; // side-only chunks use the flat layout (stream.cuh)
     bool empty() const { return nrows == 0; }
-    uint32_t main_bytes(uint32_t vs) const { return chunk_main_bytes(nrows, nother, nsiderows, nside, payload, vs); }
+    bool is_flat() const { return allow_flat && ntiles == 0 && nother == 0 && payload == 0; }
+    uint32_t main_bytes(uint32_t vs) const
+    {
+        return is_flat() ? flat_chunk_main_bytes(nrows, nside, vs) : chunk_main_bytes(nrows, nother, nsiderows, nside, payload, vs);
+    }
     // budget check: the chunk with lists as long as its own (the lists it really carries are those
     // of the chunk the same warp processes next; the stage stride is widened afterwards if needed)
     uint32_t bytes(uint32_t vs) const { return main_bytes(vs) + list_bytes(ntiles, nside); }
     uint32_t xbytes(uint32_t vs) const { return ntiles * 16u * vs + nside * vs; }
     void add(const ChunkAcc &o)
     {
+        allow_flat = allow_flat || o.allow_flat;
         nrows += o.nrows;
         ntiles += o.ntiles;
         nother += o.nother;
@@ -881,7 +1005,9 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
     std::vector<int> split_tab; // 4 ints per split row
     items.reserve((size_t)tilem + 16);
     int64_t nslots = 0;
+    const bool allow_flat = !(P->flags & TILESPMV_PLAN_NO_FLAT_SIDE);
     ChunkAcc acc;
+    acc.allow_flat = allow_flat;
     std::vector<uint32_t> ch_main, ch_nt, ch_ns; // per chunk: bytes without lists, stream tiles, side entries
     auto close_chunk = [&]() {
         if (acc.empty())
@@ -891,6 +1017,7 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
         ch_ns.push_back(acc.nside);
         chunk_item0.push_back((long long)items.size());
         acc = ChunkAcc();
+        acc.allow_flat = allow_flat;
     };
     chunk_item0.push_back(0);
     // does block row b fit a chunk on its own?  (rows that do not are cut into pieces below)
@@ -898,6 +1025,7 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
         const int ns = row_s0[b + 1] - row_s0[b];
         const long long pay_ll = (long long)ell_group_bytes((uint32_t)row_nsr[b], vs) + row_other_bytes(b);
         one = ChunkAcc();
+        one.allow_flat = allow_flat;
         one.nrows = 1;
         one.ntiles = (uint32_t)row_nt[b];
         one.nother = (uint32_t)row_other_count(b);
@@ -969,7 +1097,8 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
         {
             ChunkAcc trial = acc;
             trial.add(one);
-            if (trial.bytes(vs) > C || trial.xbytes(vs) > X || trial.nrows > 1000u || trial.ntiles > 256u)
+            if (trial.bytes(vs) > C || trial.xbytes(vs) > X || trial.nrows > (trial.is_flat() ? (uint32_t)FLAT_MAX_ROWS : 1000u) ||
+                trial.ntiles > 256u)
             {
                 close_chunk();
                 trial = one;
@@ -1007,7 +1136,7 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
                     const uint32_t t_no = (uint32_t)(h_oc[te + 1 - ta] - h_oc[te - ta]);
                     const uint32_t t_nsr = (uint32_t)(h_ws[te + 1 - ta] - h_ws[te - ta]);
                     const uint32_t t_ob = (uint32_t)(h_ob[te + 1 - ta] - h_ob[te - ta]);
-                    ChunkAcc trial;
+                    ChunkAcc trial; // pieces with stream tiles are never flat
                     trial.nrows = 1;
                     trial.ntiles = p_nt + is_tile;
                     trial.nother = p_no + t_no;
@@ -1035,8 +1164,9 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
         }
         if (ns > 0)
         {
-            const uint32_t fixed = CHUNK_OFF_ROWS + 16u + pad16(SIDEHDR_BYTES) + 16u + 16u; // header, rec, side header, two list paddings
-            uint32_t max_side = (C - fixed) / (4u + vs);
+            // header, rec, side header (or the flat layout's lens + long-row table padding), value / list paddings
+            const uint32_t fixed = CHUNK_OFF_ROWS + 16u + pad16(SIDEHDR_BYTES) + 16u + 16u + (allow_flat ? 32u : 0u);
+            uint32_t max_side = (C - fixed) / (4u + vs + (allow_flat ? 1u : 0u));
             if (max_side > X / vs)
                 max_side = X / vs;
             for (int s0 = row_s0[b]; s0 < row_s0[b + 1]; s0 += (int)max_side)
@@ -1195,6 +1325,7 @@ static int plan_build_t(const tilespmv_dmat *dm, const PlanSource &src, tilespmv
         a.nw = P->nw;
         a.stages = P->stages;
         a.head_stride = P->head_stride;
+        a.allow_flat = allow_flat ? 1 : 0;
         a.side_long_row = SIDE_LONG_ROW;
         if (const char *e = getenv("TILESPMV_SIDE_LONG_ROW")) // experiments
             a.side_long_row = atoi(e);

@@ -31,6 +31,19 @@
 //     Carrying them one chunk early lets the warp stage the x operand of chunk k+1 while it works
 //     on chunk k without chunk k+1 having arrived, so two TMA stages per warp suffice.  The lists
 //     of each warp's first chunk live in a small separate array (plan.head).
+// FLAT chunks.  A chunk whose block rows hold NO stream tile -- only extracted (side) entries: every chunk of a uniform
+// random matrix, of an x-panel sub-plan, most chunks of a power-law graph -- uses a second layout (CHF_FLAT set in
+// ChunkHeader::nrows) made for rows with a handful of entries each, where the per-block-row bookkeeping of the general
+// path (~450 warp instructions per block row) dwarfs the arithmetic:
+//   ChunkHeader | RowRec[nrows <= 16] | len u8 [16 nrows] | FlatLong[nside / FLAT_LONG_ROW] pad 16 | val T[nside] pad 16 | lists
+// The 16 nrows local rows are processed 32 at a time ("rounds": lane = row).  Inside a round the entries are stored
+// slot-major WITHOUT padding (jagged diagonals): first entry 0 of every row that has one, rows ascending, then entry 1
+// of every row that has two, ...; the kernel finds its position with one ballot + popc per slot, all loads of a slot are
+// contiguous (conflict-free), every lane sums its own row in input order and the 32 y values leave as two 128-byte
+// stores -- no shuffles, no atomics, no per-row headers.  Rows with >= FLAT_LONG_ROW entries (pieces of hub rows) have
+// len = 0 there; their entries follow the rounds in row order and are summed by the whole warp (FlatLong records).
+// Header fields in a flat chunk: off_sidehdr = offset of len[], off_payload = offset of FlatLong[], off_sideval =
+// offset of val[], off_odesc = number of FlatLong records.  The x-staging list of the chunk is in the same order as val.
 // Nibble parity is TILE-LOCAL here (element e sits in byte e/2, high nibble when e is even); the
 // reference's global-position parity (csr2tile.h:973, :982) only exists in Tile_matrix.
 // COO tiles are not in the stream as tiles: their nonzeros live in the side part exactly once
@@ -59,6 +72,16 @@ struct ChunkHeader // 32 B, read by the kernel as two 128-bit shared-memory load
 };
 static_assert(sizeof(ChunkHeader) == 32, "ChunkHeader must be 32 bytes");
 constexpr uint32_t CHF_PARTIAL_X = 1u; // some x segment sticks out past colA (zero-filled staging path)
+constexpr uint32_t CHF_FLAT = 0x8000u; // bit of ChunkHeader::nrows: side-only chunk in the flat layout
+constexpr int FLAT_MAX_ROWS = 16;      // block rows per flat chunk (8 rounds of 32 local rows)
+constexpr int FLAT_LONG_ROW = 32;      // local rows with at least this many entries are summed by the whole warp
+struct FlatLong                        // 8 B
+{
+    uint16_t row;   // local row of the chunk (block-row ordinal * 16 + row)
+    uint16_t start; // first entry (index into val[] / the staged x)
+    uint16_t count;
+    uint16_t pad;
+};
 constexpr uint32_t CHUNK_OFF_ROWS = 32;
 
 struct RowRec // 16 B, one 128-bit shared-memory load
@@ -129,6 +152,11 @@ __host__ __device__ inline uint32_t chunk_main_bytes(uint32_t nrows, uint32_t no
 {
     return CHUNK_OFF_ROWS + 16u * nrows + pad16(8u * nother) + pad16(SIDEHDR_BYTES * nsiderows) + pad16(vs * nside) +
            payload; // payload parts are multiples of 16
+}
+// the same for a flat chunk (nside extracted nonzeros in nrows block rows, no stream tile)
+__host__ __device__ inline uint32_t flat_chunk_main_bytes(uint32_t nrows, uint32_t nside, uint32_t vs)
+{
+    return CHUNK_OFF_ROWS + 16u * nrows + 16u * nrows + pad16(8u * (nside / (uint32_t)FLAT_LONG_ROW)) + pad16(vs * nside);
 }
 // head record of a warp's first chunk (plan.head): 16-byte header {ntiles | nside << 16, flags} + lists
 constexpr uint32_t HEAD_HDR_BYTES = 16;

@@ -59,8 +59,9 @@ class ShardedSpMV:
         self.val_dtype = self.dm.val_dtype
         kw = dict(plan_kwargs or {})
         opts = _capi.PlanOptions(kw.get("chunk_bytes", 0), kw.get("xstage_bytes", 0), kw.get("ctas_per_sm", 0), kw.get("stages", 0),
-                                 kw.get("max_warps", 0), 0 if kw.get("csr_groups", True) else _capi.PLAN_NO_CSR_GROUPS,
-                                 kw.get("xpanel_bytes", 0))
+                                 kw.get("max_warps", 0),
+                                 (0 if kw.get("csr_groups", True) else _capi.PLAN_NO_CSR_GROUPS) |
+                                 (0 if kw.get("flat_side", True) else _capi.PLAN_NO_FLAT_SIDE), kw.get("xpanel_bytes", 0))
         cuts = (C.c_int64 * (comm.nranks + 1))(*([r[0] for r in rows] + [rows[-1][1]]))
         h = C.c_void_p()
         _capi.check(L.tilespmv_dist_create(comm.handle, self.dm.handle, cuts, C.byref(opts),
