@@ -93,6 +93,8 @@ struct tilespmv_dist
     bool peer_mapped[tsp::COMM_MAX_RANKS] = {false};
     int peer_device[tsp::COMM_MAX_RANKS] = {0};
     cudaStream_t s_comm = nullptr, s_main = nullptr; // copy stream / the stream the loop itself runs on
+    cudaStream_t s_peer[tsp::COMM_MAX_RANKS] = {nullptr}; // halo exchange: one copy stream per peer (the copies have no order)
+    cudaEvent_t ev_peer[tsp::COMM_MAX_RANKS] = {nullptr};
     cudaEvent_t ev_user = nullptr, ev_done = nullptr; // hand-over between the caller's stream and s_main
     // the enqueued work of one call (all iterations, both streams) captured into a CUDA graph, keyed by its shape
     struct GraphEntry
@@ -132,6 +134,13 @@ struct tilespmv_dist
         for (cudaStream_t st : {s_comm, s_main})
             if (st)
                 cudaStreamDestroy(st);
+        for (int r = 0; r < tsp::COMM_MAX_RANKS; r++)
+        {
+            if (ev_peer[r])
+                cudaEventDestroy(ev_peer[r]);
+            if (s_peer[r])
+                cudaStreamDestroy(s_peer[r]);
+        }
         delete plan;
     }
 };
@@ -650,6 +659,13 @@ static int dist_create(tilespmv_comm *c, const tilespmv_dmat *dm, const int64_t 
             set_error("dist_create: cudaEventCreate failed");
             return fail(TILESPMV_ERR_CUDA);
         }
+    for (int r = 0; r < R; r++)
+        if (r != me && (cudaStreamCreateWithFlags(&d->s_peer[r], cudaStreamNonBlocking) != cudaSuccess ||
+                        cudaEventCreateWithFlags(&d->ev_peer[r], cudaEventDisableTiming) != cudaSuccess))
+        {
+            set_error("dist_create: cudaStreamCreate failed");
+            return fail(TILESPMV_ERR_CUDA);
+        }
     *out = d;
     return TILESPMV_OK;
 }
@@ -832,19 +848,24 @@ static int iterate_halo(tilespmv_dist *d, int niters, cudaStream_t s)
         TSP_TRY(launch_units(d, xbuf(d, me, sb), xbuf(d, me, db), s, true));
         TSP_CUDA(cudaEventRecord(d->ev_kernel[i & 1], s));
         TSP_TRY(flag_signal(d, DIST_OFF_A, peers, e + 1, s));
-        // ---- background replication of everything the kernel did not store itself ----
+        // ---- background replication of everything the kernel did not store itself: the copies to different peers
+        //      have no order among them, so every peer gets its own stream (copy engines run them concurrently) ----
         TSP_CUDA(cudaStreamWaitEvent(d->s_comm, d->ev_kernel[i & 1], 0));
         for (int k = 1; k < R; k++)
         {
             const int dst = (me - k + R) % R;
-            TSP_TRY(flag_wait(d, DIST_OFF_A, 1u << dst, e, d->s_comm));
+            cudaStream_t sp = d->s_peer[dst];
+            TSP_CUDA(cudaStreamWaitEvent(sp, d->ev_kernel[i & 1], 0));
+            TSP_TRY(flag_wait(d, DIST_OFF_A, 1u << dst, e, sp));
             const long long seg[2][2] = {{0, out_lo[dst]}, {out_hi[dst], d->m_local}};
             for (int g = 0; g < 2; g++)
                 if (seg[g][1] > seg[g][0])
                     TSP_CUDA(cudaMemcpyPeerAsync(xbuf(d, dst, db) + slice_off + (size_t)seg[g][0] * vs, d->peer_device[dst],
                                                  xbuf(d, me, db) + slice_off + (size_t)seg[g][0] * vs, d->comm->device,
-                                                 (size_t)(seg[g][1] - seg[g][0]) * vs, d->s_comm));
-            TSP_TRY(flag_signal(d, DIST_OFF_D, 1u << dst, e + 1, d->s_comm));
+                                                 (size_t)(seg[g][1] - seg[g][0]) * vs, sp));
+            TSP_TRY(flag_signal(d, DIST_OFF_D, 1u << dst, e + 1, sp));
+            TSP_CUDA(cudaEventRecord(d->ev_peer[dst], sp));
+            TSP_CUDA(cudaStreamWaitEvent(d->s_comm, d->ev_peer[dst], 0));
         }
         TSP_CUDA(cudaEventRecord(d->ev_push[i & 1], d->s_comm));
         d->ev_push_valid[i & 1] = true;
