@@ -338,12 +338,13 @@ def test_config4_rmat_scale_22_fp32_hub_rows():
 @pytest.mark.parametrize("seed", range(24))
 def test_random_matrices_all_plan_variants(seed):
     """Differential test: conversion bit-exact against the oracle, y against tilespmv_cpu, for every plan variant
-    (CSR groups on / off, x panels, tiny chunks that cut rows, HYB rule) on random structure."""
+    (CSR groups on / off, x panels, tiny chunks that cut rows, flat side chunks on / off, HYB rule) on random structure."""
     rng = np.random.default_rng(1000 + seed)
     case = random_case(rng)
     precision = "f64" if seed % 3 else "f32"
     variants = [dict(), dict(csr_groups=False), dict(xpanel_bytes=256), dict(chunk_bytes=2560, xstage_bytes=128),
-                dict(chunk_bytes=2560, xstage_bytes=256, xpanel_bytes=512, csr_groups=False)]
+                dict(chunk_bytes=2560, xstage_bytes=256, xpanel_bytes=512, csr_groups=False), dict(flat_side=False),
+                dict(flat_side=False, xpanel_bytes=384, chunk_bytes=2560, xstage_bytes=256)]
     check_matrix(case, precision, plan_kwargs=variants[seed % len(variants)], enable_hyb=seed % 4 == 0)
     check_matrix(case, precision, plan_kwargs=variants[(seed + 1) % len(variants)])
 
