@@ -826,6 +826,9 @@ def _d2d(dst, src, nbytes):
 
 
 def main():
+    # more hardware queues than the default 8: the multi-GPU loop uses a handful of streams next to torch's own, and
+    # streams that share a queue serialise (must be set before the CUDA context exists)
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)   # BENCH_REPEAT of the reference (common.h:16-18)
