@@ -563,6 +563,12 @@ def run_multi(args, rank, world, local_rank):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         verify[mode]["verified"] = bool(flag.item())
     del xs, xr, br
+    allv = [None] * world
+    dist.all_gather_object(allv, {mo: {k: v for k, v in verify[mo].items() if k in ("error", "ok", "identical_on_all_ranks")} for mo in verify})
+    for mo in verify:
+        bad = {r: allv[r][mo] for r in range(world) if allv[r][mo].get("error") or not allv[r][mo].get("ok")}
+        if bad:
+            verify[mo]["failing_ranks"] = {str(r): v for r, v in bad.items()}
     good = [mo for mo in MODES if verify[mo].get("verified")]
     if not good or not ok_spmv:
         if rank == 0:
@@ -826,9 +832,6 @@ def _d2d(dst, src, nbytes):
 
 
 def main():
-    # more hardware queues than the default 8: the multi-GPU loop uses a handful of streams next to torch's own, and
-    # streams that share a queue serialise (must be set before the CUDA context exists)
-    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)   # BENCH_REPEAT of the reference (common.h:16-18)
