@@ -39,6 +39,7 @@ UNIT = "GFLOP/s"
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 NVLINK_PEER_GBS = 770.0    # measured peer copy per direction (B200_PROFILING.md)
 MODES = ("nccl", "fused", "pipelined", "halo")
+DEFAULT_MODES = ("nccl", "fused", "pipelined")  # halo: --with-halo (no gain over fused on this pool)
 SEGMENT = 50               # x <- A*x restarts from x0 every SEGMENT iterations (keeps the iterates finite for any K)
 
 
@@ -544,7 +545,8 @@ def run_multi(args, rank, world, local_rank):
         xr, br = torch.cat(parts), torch.cat(bparts)
     del A, Aabs, y_chk, bound, parts, bparts
     verify, xs = {}, {}
-    for mode in MODES:
+    modes = MODES if (args.with_halo or args.exchange == "halo") else DEFAULT_MODES
+    for mode in modes:
         try:
             xs[mode] = result(sp.iterate(x0.data_ptr(), KV, mode=mode, stream=stream))
             sp.sync(stream)
@@ -554,7 +556,7 @@ def run_multi(args, rank, world, local_rank):
             verify[mode] = {"max_err_over_bound": err, "ok": err <= 1e-10, "identical_on_all_ranks": bool(torch.equal(same, xs[mode]))}
         except Exception as e:
             verify[mode] = {"ok": False, "error": str(e)[:300]}
-    ref_mode = next((mo for mo in MODES if mo in xs), None)
+    ref_mode = next((mo for mo in modes if mo in xs), None)
     for mode in xs:
         verify[mode]["bitwise_equal_to_" + ref_mode] = bool(torch.equal(xs[mode], xs[ref_mode]))
     for mode in verify:  # a rank-local failure fails the mode everywhere
@@ -569,7 +571,7 @@ def run_multi(args, rank, world, local_rank):
         bad = {r: allv[r][mo] for r in range(world) if allv[r][mo].get("error") or not allv[r][mo].get("ok")}
         if bad:
             verify[mo]["failing_ranks"] = {str(r): v for r, v in bad.items()}
-    good = [mo for mo in MODES if verify[mo].get("verified")]
+    good = [mo for mo in modes if verify[mo].get("verified")]
     if not good or not ok_spmv:
         if rank == 0:
             sys.stderr.write(f"bench: verification failed: spmv {ok_spmv}, {json.dumps(verify)}\n")
@@ -849,6 +851,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-one-gpu", action="store_true")
     ap.add_argument("--no-weak", action="store_true")
+    ap.add_argument("--with-halo", action="store_true", help="also verify / time the halo exchange")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
