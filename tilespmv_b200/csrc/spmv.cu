@@ -750,49 +750,91 @@ __device__ __forceinline__ void store_row(const SpmvArgs<T> &a, uint32_t dest, i
     }
 }
 
-template <class T>
-__device__ __forceinline__ void process_chunk_flat(uint32_t st_s, uint32_t xb_s, const SpmvArgs<T> &a, int lane)
+// SPLIT = false: 32 local rows per round, one lane per row.  SPLIT = true (chunks of ONE block row: 16 rows with many
+// entries each, e.g. 20 per row in a uniform random matrix): two lanes per row -- lane (row, h) takes the slots j with
+// j mod 2 == h -- so that all 32 lanes work, and the two halves are added with one shuffle.
+template <class T, bool SPLIT>
+__device__ __forceinline__ void process_chunk_flat_t(uint32_t st_s, uint32_t xb_s, const SpmvArgs<T> &a, int lane)
 {
     constexpr uint32_t VS = (uint32_t)sizeof(T);
+    constexpr int RPR = SPLIT ? 16 : 32; // rows per round
     const uint4 ha = lds_v4(st_s);
     const int nrows16 = (int)(ha.x & 0x7fffu) * TS;
     uint32_t nlong = ha.z >> 16;                       // off_odesc: number of FlatLong records
     const uint32_t lens_s = st_s + (ha.w & 0xffffu);   // off_sidehdr: len[16 nrows]
     const uint32_t vals_s = st_s + (ha.w >> 16);       // off_sideval: val[nside]
     uint32_t long_s = st_s + lds_u32(st_s + 16u);      // off_payload: FlatLong[]
-    const uint32_t lt = (1u << lane) - 1u;
+    const int rl = SPLIT ? (lane & 15) : lane;         // row of the round this lane works on
+    const uint32_t h = SPLIT ? (uint32_t)(lane >> 4) : 0u;
+    const uint32_t lt = (1u << rl) - 1u, rowbits = SPLIT ? 0xffffu : 0xffffffffu;
     uint32_t pos = 0;
 #pragma unroll 1
-    for (int rd = 0; rd * 32 < nrows16; rd++)
+    for (int rd = 0; rd * RPR < nrows16; rd++)
     {
-        const int rho = rd * 32 + lane;
+        const int rho = rd * RPR + rl;
         const bool live = rho < nrows16;
         const uint32_t len = live ? lds_u8(lens_s + (uint32_t)rho) : 0u;
         const uint4 rec = lds_v4(st_s + CHUNK_OFF_ROWS + 16u * (uint32_t)((live ? rho : nrows16 - 1) >> 4));
         T acc = 0;
-#pragma unroll 1
-        for (uint32_t j = 0;; j += 2u) // two slots per trip: four loads in flight
+        if (!SPLIT)
         {
-            const unsigned m0 = __ballot_sync(0xffffffffu, len > j);
-            if (!m0)
-                break;
-            const unsigned m1 = __ballot_sync(0xffffffffu, len > j + 1u);
-            const uint32_t n0 = (uint32_t)__popc(m0);
-            const uint32_t p0 = pos + (uint32_t)__popc(m0 & lt), p1 = pos + n0 + (uint32_t)__popc(m1 & lt);
-            T v0 = 0, x0 = 0, v1 = 0, x1 = 0;
-            if (len > j)
+#pragma unroll 1
+            for (uint32_t j = 0;; j += 2u) // two slots per trip: four loads in flight
             {
-                v0 = SL<T>::ld(mad_u32(p0, VS, vals_s));
-                x0 = SL<T>::ld(mad_u32(p0, VS, xb_s));
+                const unsigned m0 = __ballot_sync(0xffffffffu, len > j);
+                if (!m0)
+                    break;
+                const unsigned m1 = __ballot_sync(0xffffffffu, len > j + 1u);
+                const uint32_t n0 = (uint32_t)__popc(m0);
+                const uint32_t p0 = pos + (uint32_t)__popc(m0 & lt), p1 = pos + n0 + (uint32_t)__popc(m1 & lt);
+                T v0 = 0, x0 = 0, v1 = 0, x1 = 0;
+                if (len > j)
+                {
+                    v0 = SL<T>::ld(mad_u32(p0, VS, vals_s));
+                    x0 = SL<T>::ld(mad_u32(p0, VS, xb_s));
+                }
+                if (len > j + 1u)
+                {
+                    v1 = SL<T>::ld(mad_u32(p1, VS, vals_s));
+                    x1 = SL<T>::ld(mad_u32(p1, VS, xb_s));
+                }
+                acc = fma_t<T>(v0, x0, acc);
+                acc = fma_t<T>(v1, x1, acc);
+                pos += n0 + (uint32_t)__popc(m1);
             }
-            if (len > j + 1u)
+        }
+        else
+        {
+#pragma unroll 1
+            for (uint32_t j = 0;; j += 4u) // four slots per trip, two per half: four loads in flight per lane
             {
-                v1 = SL<T>::ld(mad_u32(p1, VS, vals_s));
-                x1 = SL<T>::ld(mad_u32(p1, VS, xb_s));
+                const unsigned m0 = __ballot_sync(0xffffffffu, len > j) & rowbits;
+                if (!m0)
+                    break;
+                const unsigned m1 = __ballot_sync(0xffffffffu, len > j + 1u) & rowbits;
+                const unsigned m2 = __ballot_sync(0xffffffffu, len > j + 2u) & rowbits;
+                const unsigned m3 = __ballot_sync(0xffffffffu, len > j + 3u) & rowbits;
+                const uint32_t n0 = (uint32_t)__popc(m0), n1 = (uint32_t)__popc(m1), n2 = (uint32_t)__popc(m2);
+                // this lane's two slots: j + h and j + 2 + h
+                const unsigned ma = h ? m1 : m0, mb = h ? m3 : m2;
+                const uint32_t pa = pos + (h ? n0 : 0u) + (uint32_t)__popc(ma & lt);
+                const uint32_t pb = pos + n0 + n1 + (h ? n2 : 0u) + (uint32_t)__popc(mb & lt);
+                T v0 = 0, x0 = 0, v1 = 0, x1 = 0;
+                if ((ma >> rl) & 1u)
+                {
+                    v0 = SL<T>::ld(mad_u32(pa, VS, vals_s));
+                    x0 = SL<T>::ld(mad_u32(pa, VS, xb_s));
+                }
+                if ((mb >> rl) & 1u)
+                {
+                    v1 = SL<T>::ld(mad_u32(pb, VS, vals_s));
+                    x1 = SL<T>::ld(mad_u32(pb, VS, xb_s));
+                }
+                acc = fma_t<T>(v0, x0, acc);
+                acc = fma_t<T>(v1, x1, acc);
+                pos += n0 + n1 + n2 + (uint32_t)__popc(m3);
             }
-            acc = fma_t<T>(v0, x0, acc);
-            acc = fma_t<T>(v1, x1, acc);
-            pos += n0 + (uint32_t)__popc(m1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 16); // the two halves of every row
         }
         // rows of this round with >= FLAT_LONG_ROW entries (pieces of hub rows): the whole warp sums them
 #pragma unroll 1
@@ -800,7 +842,7 @@ __device__ __forceinline__ void process_chunk_flat(uint32_t st_s, uint32_t xb_s,
         {
             const uint32_t w0 = lds_u32(long_s), cnt = lds_u16(long_s + 4u);
             const uint32_t lrow = w0 & 0xffffu, s = w0 >> 16;
-            if (lrow >= (uint32_t)(rd + 1) * 32u)
+            if (lrow >= (uint32_t)(rd + 1) * (uint32_t)RPR)
                 break;
             T c0 = 0, c1 = 0, c2 = 0, c3 = 0;
 #pragma unroll 1
@@ -821,14 +863,23 @@ __device__ __forceinline__ void process_chunk_flat(uint32_t st_s, uint32_t xb_s,
             c += __shfl_xor_sync(0xffffffffu, c, 4);
             c += __shfl_xor_sync(0xffffffffu, c, 2);
             c += __shfl_xor_sync(0xffffffffu, c, 1);
-            if ((uint32_t)lane == (lrow & 31u))
+            if ((uint32_t)lane == (lrow & (uint32_t)(RPR - 1)))
                 acc += c;
             long_s += 8u;
             nlong--;
         }
-        if (live && (rho & 15) < (int)(rec.z & 0xffu))
+        if (live && h == 0u && (rho & 15) < (int)(rec.z & 0xffu))
             store_row<T>(a, rec.x, rho & 15, acc);
     }
+}
+
+template <class T>
+__device__ __forceinline__ void process_chunk_flat(uint32_t st_s, uint32_t xb_s, const SpmvArgs<T> &a, int lane)
+{
+    if ((lds_u16(st_s) & 0x7fffu) == 1u) // one block row: two lanes per row
+        process_chunk_flat_t<T, true>(st_s, xb_s, a, lane);
+    else
+        process_chunk_flat_t<T, false>(st_s, xb_s, a, lane);
 }
 
 template <class T, int SPMV_STAGES, int MAXREG>
