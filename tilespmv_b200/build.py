@@ -119,7 +119,8 @@ def _build_cuda_locked(force, verbose, extra, flags):
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, cuda_sources()))
     tmp = LIB_CUDA + ".tmp%d" % os.getpid()
-    cmd = [NVCC, "-shared", "-ccbin", GPP] + objs + ["-o", tmp] + LINK_LIBS
+    # the arch on the link line too: without it nvcc adds an empty default-arch (sm_52) image and warns about it
+    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", GPP] + objs + ["-o", tmp] + LINK_LIBS
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)

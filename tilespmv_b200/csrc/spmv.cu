@@ -330,7 +330,10 @@ struct Vec2<float>
 // selects every 4th slot-row / element, so a warp covers 4 slot-rows (64 values) per iteration
 // with one 128-bit shared-memory load per lane.
 // ---------------------------------------------------------------------------------------------
-template <class T>
+// PLAIN = the launch has no peers and does not accumulate (every single-GPU y = A*x): the epilogue is one select of the
+// destination (y / partial-sum scratch) and one store on 32-bit row arithmetic instead of the general path's chain of
+// warp-uniform branches (47 -> ~12 warp instructions per block row)
+template <class T, bool PLAIN>
 __device__ __forceinline__ void process_chunk(const unsigned char *st, uint32_t st_s, const T *xb, uint32_t xb_s,
                                               uint32_t zero_s, const SpmvArgs<T> &a, int lane)
 {
@@ -699,7 +702,15 @@ __device__ __forceinline__ void process_chunk(const unsigned char *st, uint32_t 
             acc += __shfl_xor_sync(0xffffffffu, acc, 16);
             const int rowlen = (int)(rec.z & 0xffu);
             const int r = 2 * p + (g & 1);
-            if (lane < 16 && r < rowlen)
+            if (PLAIN)
+            {
+                if (lane < 16 && r < rowlen)
+                {
+                    T *base = (rec.x & ROW_PARTIAL) ? a.scratch : a.y;
+                    base[(rec.x & ~ROW_PARTIAL) * (uint32_t)TS + (uint32_t)r] = acc; // rows / slots < 2^32 / 16 (rowA is an int)
+                }
+            }
+            else if (lane < 16 && r < rowlen)
             {
                 const bool partial = (rec.x & ROW_PARTIAL) != 0;
                 const size_t row = (size_t)(rec.x & ~ROW_PARTIAL) * TS + r;
@@ -731,9 +742,15 @@ __device__ __forceinline__ void process_chunk(const unsigned char *st, uint32_t 
 // conflict-free, every lane sums its own row in input order and the round's 32 y values leave as two 128-byte stores.
 // ~30 + 12 * (longest row) warp instructions per round instead of ~450 per block row in process_chunk.
 // ---------------------------------------------------------------------------------------------
-template <class T>
+template <class T, bool PLAIN>
 __device__ __forceinline__ void store_row(const SpmvArgs<T> &a, uint32_t dest, int r, T acc)
 {
+    if (PLAIN)
+    {
+        T *base = (dest & ROW_PARTIAL) ? a.scratch : a.y;
+        base[(dest & ~ROW_PARTIAL) * (uint32_t)TS + (uint32_t)r] = acc;
+        return;
+    }
     const bool partial = (dest & ROW_PARTIAL) != 0;
     const size_t row = (size_t)(dest & ~ROW_PARTIAL) * TS + r;
     if (a.accumulate && !partial && a.npeers == 0)
@@ -753,7 +770,7 @@ __device__ __forceinline__ void store_row(const SpmvArgs<T> &a, uint32_t dest, i
 // SPLIT = false: 32 local rows per round, one lane per row.  SPLIT = true (chunks of ONE block row: 16 rows with many
 // entries each, e.g. 20 per row in a uniform random matrix): two lanes per row -- lane (row, h) takes the slots j with
 // j mod 2 == h -- so that all 32 lanes work, and the two halves are added with one shuffle.
-template <class T, bool SPLIT>
+template <class T, bool SPLIT, bool PLAIN>
 __device__ __forceinline__ void process_chunk_flat_t(uint32_t st_s, uint32_t xb_s, const SpmvArgs<T> &a, int lane)
 {
     constexpr uint32_t VS = (uint32_t)sizeof(T);
@@ -869,20 +886,20 @@ __device__ __forceinline__ void process_chunk_flat_t(uint32_t st_s, uint32_t xb_
             nlong--;
         }
         if (live && h == 0u && (rho & 15) < (int)(rec.z & 0xffu))
-            store_row<T>(a, rec.x, rho & 15, acc);
+            store_row<T, PLAIN>(a, rec.x, rho & 15, acc);
     }
 }
 
-template <class T>
+template <class T, bool PLAIN>
 __device__ __forceinline__ void process_chunk_flat(uint32_t st_s, uint32_t xb_s, const SpmvArgs<T> &a, int lane)
 {
     if ((lds_u16(st_s) & 0x7fffu) == 1u) // one block row: two lanes per row
-        process_chunk_flat_t<T, true>(st_s, xb_s, a, lane);
+        process_chunk_flat_t<T, true, PLAIN>(st_s, xb_s, a, lane);
     else
-        process_chunk_flat_t<T, false>(st_s, xb_s, a, lane);
+        process_chunk_flat_t<T, false, PLAIN>(st_s, xb_s, a, lane);
 }
 
-template <class T, int SPMV_STAGES, int MAXREG>
+template <class T, int SPMV_STAGES, int MAXREG, bool PLAIN>
 __global__ void __maxnreg__(MAXREG) tile_spmv_kernel(const SpmvArgs<T> a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -977,9 +994,9 @@ __global__ void __maxnreg__(MAXREG) tile_spmv_kernel(const SpmvArgs<T> a)
         cp_async_wait<1>(); // this lane's x copies of chunk k have landed ...
         __syncwarp();       // ... and so have everybody else's
         if (lds_u16(st_s) & CHF_FLAT) // warp-uniform: a chunk of extracted entries only
-            process_chunk_flat<T>(st_s, xcur, a, lane);
+            process_chunk_flat<T, PLAIN>(st_s, xcur, a, lane);
         else
-            process_chunk<T>(wbase + (size_t)st * cb, st_s, reinterpret_cast<const T *>(xbase + (size_t)(k & 1) * xsb), xcur,
+            process_chunk<T, PLAIN>(wbase + (size_t)st * cb, st_s, reinterpret_cast<const T *>(xbase + (size_t)(k & 1) * xsb), xcur,
                              zero_s, a, lane);
         __syncwarp(); // all lanes are done reading stage st and x buffer k&1
         if (lane == 0 && issue.y != 0u)
@@ -1072,14 +1089,20 @@ static size_t warp_smem_bytes(const tilespmv_plan *P)
     return (size_t)P->stages * P->stage_stride + 2 * (size_t)P->xstage_bytes;
 }
 
-template <class T>
-static const void *kernel_for(int stages, int warps)
+template <class T, bool PLAIN>
+static const void *kernel_for_t(int stages, int warps)
 {
     if (stages == 2)
-        return warps > 20 ? (const void *)tile_spmv_kernel<T, 2, SPMV_REGS_LO> : (const void *)tile_spmv_kernel<T, 2, SPMV_REGS_HI>;
+        return warps > 20 ? (const void *)tile_spmv_kernel<T, 2, SPMV_REGS_LO, PLAIN> : (const void *)tile_spmv_kernel<T, 2, SPMV_REGS_HI, PLAIN>;
     if (stages == 3)
-        return (const void *)tile_spmv_kernel<T, 3, 128>;
-    return (const void *)tile_spmv_kernel<T, 4, 128>;
+        return (const void *)tile_spmv_kernel<T, 3, 128, PLAIN>;
+    return (const void *)tile_spmv_kernel<T, 4, 128, PLAIN>;
+}
+// plain = no peers, no accumulation: the specialised epilogue
+template <class T>
+static const void *kernel_for(int stages, int warps, bool plain)
+{
+    return plain ? kernel_for_t<T, true>(stages, warps) : kernel_for_t<T, false>(stages, warps);
 }
 
 template <class T>
@@ -1087,14 +1110,17 @@ static int set_kernel_attrs(int stages, int warps, int smem_optin)
 {
     // the attribute is per kernel, not per plan: always raise it to the device limit so that plans
     // with different shared-memory footprints can coexist in one process
-    const void *fn = kernel_for<T>(stages, warps);
-    TSP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
-    // prefer L1: the driver still has to provide the dynamic shared memory a launch asks for, so streaming plans
-    // (221 KB) get the 228 KB carve-out as before, while gather-bound plans (<= gather_smem_cap) leave >= 92 KB of L1
     int carve = 0;
     if (const char *e = getenv("TILESPMV_CARVEOUT")) // experiments only
         carve = atoi(e);
-    TSP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    for (int plain = 0; plain < 2; plain++)
+    {
+        const void *fn = kernel_for<T>(stages, warps, plain != 0);
+        TSP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+        // prefer L1: the driver still has to provide the dynamic shared memory a launch asks for, so streaming plans
+        // (221 KB) get the 228 KB carve-out as before, while gather-bound plans (<= gather_smem_cap) leave >= 92 KB of L1
+        TSP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    }
     return TILESPMV_OK;
 }
 
@@ -1209,9 +1235,11 @@ static int plan_launch_one(tilespmv_plan *P, const T *x, T *y, cudaStream_t s, i
         a.peer_hi[p] = p < npeers ? peer_hi[p] : 0;
     }
     const int grid = P->grid; // fixed at plan time: the stream's lookahead lists depend on it
+    static const bool no_plain = getenv("TILESPMV_NO_PLAIN_EPILOGUE") != nullptr; // A/B switch, read once
+    const bool plain = npeers == 0 && !a.accumulate && !no_plain;
     {
         void *args[] = {(void *)&a};
-        cudaError_t err = cudaLaunchKernel(kernel_for<T>(P->stages, P->block / 32), dim3(grid), dim3(P->block), args, (size_t)P->smem, s);
+        cudaError_t err = cudaLaunchKernel(kernel_for<T>(P->stages, P->block / 32, plain), dim3(grid), dim3(P->block), args, (size_t)P->smem, s);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         if (err != cudaSuccess)
         {
