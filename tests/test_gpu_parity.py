@@ -224,6 +224,41 @@ def test_iterate_graph_equals_a_loop_of_spmv_calls(name):
         api.Plan(api.DeviceTileMatrix.from_csr(m2, n2, rp2, ci2, v2)).iterate(xa.data_ptr(), xb.data_ptr(), 2)
 
 
+@pytest.mark.parametrize("name", ["lap2d_256", "lap3d27_48", "uniform_64k", "rmat_15"])
+def test_back_to_back_launches_see_the_previous_result(name):
+    """Consecutive launches of one stream overlap their set-up with the previous kernel's tail (programmatic dependent
+    launch: the kernel fetches its first chunks of the immutable stream, then waits for the grid dependency before it
+    touches x or y).  A chain x <- A*x issued back to back must equal the same chain with a device synchronisation after
+    every launch, bit for bit -- on the default stream and on a side stream, with sub-plans (x panels) in between."""
+    import torch
+    m, n, rp, ci, v = BIG_CASES[name]()
+    assert m == n
+    dm = api.DeviceTileMatrix.from_csr(m, n, rp, ci, v * (1.0 / 64))
+    for kw in ({}, {"xpanel_bytes": 64 * 1024}):
+        plan = api.Plan(dm, **kw)
+        x0 = torch.from_numpy(np.random.default_rng(5).uniform(-1, 1, n)).cuda()
+        niters = 12
+
+        def chain(sync_every, stream):
+            a, b = x0.clone(), torch.full_like(x0, float("nan"))
+            torch.cuda.synchronize()
+            for i in range(niters):
+                src, dst = (a, b) if i % 2 == 0 else (b, a)
+                plan.spmv(src.data_ptr(), dst.data_ptr(), stream)
+                if sync_every:
+                    torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            return (a if niters % 2 == 0 else b).clone()
+
+        want = chain(True, 0)
+        assert torch.isfinite(want).all()
+        st = torch.cuda.Stream()
+        for _ in range(3):
+            assert torch.equal(chain(False, 0), want)
+            assert torch.equal(chain(False, st.cuda_stream), want)
+        plan.destroy()
+
+
 def test_device_pointer_path_streams_and_linearity():
     """tilespmv_plan_spmv on torch device buffers and a non-default stream; A(ax+by) = aAx + bAy."""
     import torch

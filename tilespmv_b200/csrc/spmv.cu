@@ -918,24 +918,40 @@ __global__ void __maxnreg__(MAXREG) tile_spmv_kernel(const SpmvArgs<T> a)
     const int nk = gw < a.nchunks ? (int)((a.nchunks - gw + nw - 1) / nw) : 0;
     // 64 bytes of zeros behind the barriers: where predicated-off loads of the tail loops land
     const uint32_t zero_s = smem_u32(smem) + (uint32_t)(SPMV_BAR_BYTES - 64);
+    // Programmatic dependent launch: the NEXT kernel of the stream (launched with the programmatic-serialization
+    // attribute, plan_launch_one) may be scheduled as soon as every CTA of this grid has passed this point.  Its CTAs
+    // become resident when ours exit, and everything they do before their own griddepcontrol.wait below -- barrier
+    // set-up, the TMA fetches of their first chunks of the (immutable) packed stream, the head lists -- runs under this
+    // grid's tail instead of after it.  A no-op when nothing depends on this launch.
+    asm volatile("griddepcontrol.launch_dependents;");
     if (threadIdx.x < 16)
         reinterpret_cast<uint32_t *>(smem + SPMV_BAR_BYTES - 64)[threadIdx.x] = 0u;
     __syncthreads();
-    if (a.pf_bytes && lane == 0)
-    {
-        // every warp of the grid prefetches its share of the x window (4 KB pieces, fire and forget)
-        const unsigned long long per = ((a.pf_bytes + nw - 1) / nw + 4095ull) & ~4095ull;
-        unsigned long long o = (unsigned long long)gw * per;
-        const unsigned long long end = o + per < a.pf_bytes ? o + per : a.pf_bytes;
-        for (; o < end; o += 4096ull)
+    // every warp of the grid prefetches its share of the x window (4 KB pieces, fire and forget); x may be the previous
+    // kernel's output, so only after the grid dependency is resolved
+    auto prefetch_x_window = [&]() {
+        if (a.pf_bytes && lane == 0)
         {
-            const unsigned n = (unsigned)((end - o < 4096ull ? end - o : 4096ull) & ~15ull);
-            if (n)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.pf_base + o), "r"(n) : "memory");
+            const unsigned long long per = ((a.pf_bytes + nw - 1) / nw + 4095ull) & ~4095ull;
+            unsigned long long o = (unsigned long long)gw * per;
+            const unsigned long long end = o + per < a.pf_bytes ? o + per : a.pf_bytes;
+            for (; o < end; o += 4096ull)
+            {
+                const unsigned n = (unsigned)((end - o < 4096ull ? end - o : 4096ull) & ~15ull);
+                if (n)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.pf_base + o), "r"(n) : "memory");
+            }
         }
-    }
+    };
     if (nk == 0)
+    {
+        if (a.pf_bytes)
+        {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            prefetch_x_window();
+        }
         return;
+    }
 
     if (lane == 0)
     {
@@ -970,6 +986,10 @@ __global__ void __maxnreg__(MAXREG) tile_spmv_kernel(const SpmvArgs<T> a)
     {
         const uint32_t *h = reinterpret_cast<const uint32_t *>(a.head + (size_t)gw * (size_t)a.head_stride);
         const uint32_t cnt = __ldg(h), fl = __ldg(h + 1);
+        // nothing above read x or wrote y / scratch (the stream, the chunk table and the head lists never change): from
+        // here on the launch needs the results of everything before it in the stream
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        prefetch_x_window();
         stage_x<T, true>(0u, h + HEAD_HDR_BYTES / 4, (int)(cnt & 0xffffu), (int)(cnt >> 16), fl, xb0, a.x, xpiece, a.colA, lane);
         cp_async_commit();
     }
@@ -1239,7 +1259,31 @@ static int plan_launch_one(tilespmv_plan *P, const T *x, T *y, cudaStream_t s, i
     const bool plain = npeers == 0 && !a.accumulate && !no_plain;
     {
         void *args[] = {(void *)&a};
-        cudaError_t err = cudaLaunchKernel(kernel_for<T>(P->stages, P->block / 32, plain), dim3(grid), dim3(P->block), args, (size_t)P->smem, s);
+        // programmatic dependent launch (see the top of the kernel): this launch may begin while the previous kernel of
+        // the stream drains; the kernel itself waits (griddepcontrol.wait) before it touches x, y or the scratch.  Only a
+        // kernel-to-kernel edge of the same stream is relaxed; copies, events and kernels launched without the attribute
+        // (the fix-up kernels below, the flag kernels of comm.cu, the caller's own kernels) keep the full stream order.
+        // Stream captures keep the attribute (the graph gets a programmatic edge: tilespmv_plan_iterate 21.1 -> 19.8 us per
+        // iteration on config 1).  A/B switches: TILESPMV_NO_PDL=1 (never), TILESPMV_NO_PDL_IN_GRAPHS=1 (not while capturing).
+        static const int pdl_mode = getenv("TILESPMV_NO_PDL") ? 0 : (getenv("TILESPMV_NO_PDL_IN_GRAPHS") ? 1 : 2);
+        bool pdl = pdl_mode != 0;
+        if (pdl_mode == 1)
+        {
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)
+                pdl = false;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(P->block);
+        cfg.dynamicSmemBytes = (size_t)P->smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl ? 1 : 0;
+        cudaError_t err = cudaLaunchKernelExC(&cfg, kernel_for<T>(P->stages, P->block / 32, plain), args);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         if (err != cudaSuccess)
         {
