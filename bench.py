@@ -40,6 +40,10 @@ HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 NVLINK_PEER_GBS = 770.0    # measured peer copy per direction (B200_PROFILING.md)
 MODES = ("nccl", "fused", "pipelined", "halo")
 DEFAULT_MODES = ("nccl", "fused", "pipelined")  # halo: --with-halo (no gain over fused on this pool)
+GATHER_PROBE_GPS = 263.0   # scattered 8-byte loads from an L2-resident window, tools/gather_probe.cu (profiles/r01_gather_probe.log)
+LAUNCH_NOTE = ("steps are launched back to back on one stream; every launch carries the programmatic-stream-serialization attribute: "
+               "its set-up and first fetches of the (immutable) packed matrix stream overlap the previous launch's tail, and the "
+               "kernel waits for the grid dependency before it reads x or writes y (TILESPMV_NO_PDL=1 switches it off)")
 SEGMENT = 50               # x <- A*x restarts from x0 every SEGMENT iterations (keeps the iterates finite for any K)
 
 
@@ -175,14 +179,15 @@ def workload_config(wl, args, world):
         G = args.grid
         return {"workload": f"BASELINE config 2: 3-D 27-point Laplacian {G}^3 fp64 ({G ** 3} rows, ~{(3 * G - 2) ** 3 / 1e6:.0f} M nnz) on 1 GPU, "
                             "one y = A*x per step",
-                "cache": "inputs larger than L2 (packed stream ~1.07 GB vs 126 MB L2); no flush"}
+                "cache": "inputs larger than L2 (packed stream ~1.07 GB vs 126 MB L2); no flush",
+                "launch": LAUNCH_NOTE}
     n = {"c3": args.c3_rows, "c5": args.c5_rows}[wl]
     what = {"c3": f"BASELINE config 3: banded FEM-like {n} x {n}, half-bandwidth 64, 37 nnz/row (~{n * 37 / 1e6:.0f} M nnz) fp64",
             "c5": f"BASELINE config 5: uniform random {n} x {n}, 20 nnz/row ({n * 20 / 1e9:.2f} G nnz) fp64"}[wl]
     return {"workload": what + f", row-block sharded over {world} GPUs; one step = one iteration of x <- A*x incl. the all-gather of x",
             "partition": f"{world} contiguous row blocks of tiles (cuts at multiples of 16 rows), x replicated",
             "exchange": "value: the fastest verified exchange of tilespmv_dist_iterate (named in headline_exchange); `iterate` lists all three",
-            "cache": "inputs larger than L2 (packed stream per GPU > 126 MB L2); no flush"}
+            "cache": "inputs larger than L2 (packed stream per GPU > 126 MB L2); no flush", "launch": LAUNCH_NOTE}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -788,7 +793,14 @@ def run_multi(args, rank, world, local_rank):
                          "timing": "CUDA events around back-to-back SpMVs of rank 0's shard WITHOUT the exchange (kernel alone)",
                          "achieved_inside_iterate": b_alg / (ms_step * 1e-3) / 1e9,
                          "frac_inside_iterate": b_alg / (ms_step * 1e-3) / 1e9 / peak,
-                         "frac_of_nominal_8TBs": b_alg / (ms_kernel_local * 1e-3) / 1e9 / 8000.0},
+                         "frac_of_nominal_8TBs": b_alg / (ms_kernel_local * 1e-3) / 1e9 / 8000.0,
+                         "gather": ({"side_entries_rank0": int(di.nnz_side),
+                                     "achieved_G_per_s": di.nnz_side / (ms_kernel_local * 1e-3) / 1e9,
+                                     "probe_ceiling_G_per_s": GATHER_PROBE_GPS,
+                                     "frac_of_probe": di.nnz_side / (ms_kernel_local * 1e-3) / 1e9 / GATHER_PROBE_GPS,
+                                     "note": "this row block is made of extracted (side) entries: one scattered 8-byte load of x per nonzero; "
+                                             "the SM's L1 accepts ~0.92 such requests per clock (tools/gather_probe.cu), which binds before HBM does"}
+                                    if 2 * di.nnz_side > nnz_local else None)},
             "cpu_baseline": None,
             "iterate": dict(iterate, verification=verify,
                             collective={"nccl": "one in-place ncclAllGather per iteration (library-owned communicator)",
