@@ -312,6 +312,7 @@ def conversion_baseline(gpu=True):
                     "conversion_bytes": int(csr_bytes + dbytes),
                     "gpu_GBps_on_conversion_bytes": (csr_bytes + dbytes) / best_d / 1e9,
                     "speedup_vs_reference": out["reference_tile_create_s"] / best_h,
+                    "speedup_vs_reference_device_csr": out["reference_tile_create_s"] / best_d,
                     "note": "bytes = CSR read once + every Tile_matrix array written once; the GPU conversion is a sort + 13 "
                             "scans + scatter, i.e. several passes over those bytes, so this is a lower bound on its traffic"})
     return out
