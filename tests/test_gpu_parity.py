@@ -448,3 +448,9 @@ def test_plan_cache_round_trip(tmp_path, name, kw):
         api.Plan.load(bad, api.F64, m, n)
     with pytest.raises(api.TileSpMVError):
         api.Plan.load(str(tmp_path / "missing.bin"), api.F64, m, n)
+    # a damaged header that promises 2^60 bytes of payload is an I/O error, not a 2^60-byte allocation
+    blob = bytearray(open(path, "rb").read())
+    blob[24:32] = (1 << 60).to_bytes(8, "little")  # PlanFileHeader.payload_bytes
+    open(bad, "wb").write(bytes(blob))
+    with pytest.raises(api.TileSpMVError):
+        api.Plan.load(bad, api.F64, m, n)

@@ -1000,79 +1000,102 @@ const char *tilespmv_version(void) { return "tilespmv_b200 0.1.0 (sm_100a)"; }
 int64_t tilespmv_kernel_launch_count(void) { return g_launches.load(); }
 
 void Tile_create_f64(Tile_matrix_f64 *matrix, int rowA, int colA, int nnzA, int *csrRowPtrA, int *csrColIdxA, double *csrValA)
+try
 {
     clear_error();
     (void)nnzA;
     tile_create_entry<Tile_matrix_f64, double>(matrix, rowA, colA, csrRowPtrA, csrColIdxA, csrValA);
 }
+TSP_CATCH_VOID("Tile_create_f64")
 void Tile_create_f32(Tile_matrix_f32 *matrix, int rowA, int colA, int nnzA, int *csrRowPtrA, int *csrColIdxA, float *csrValA)
+try
 {
     clear_error();
     (void)nnzA;
     tile_create_entry<Tile_matrix_f32, float>(matrix, rowA, colA, csrRowPtrA, csrColIdxA, csrValA);
 }
+TSP_CATCH_VOID("Tile_create_f32")
 void Tile_destroy_f64(Tile_matrix_f64 *matrix) { tile_destroy(matrix); }
 void Tile_destroy_f32(Tile_matrix_f32 *matrix) { tile_destroy(matrix); }
 
 int tilespmv_prepare_f64(const Tile_matrix_f64 *matrix, int *ptroffset1, int *ptroffset2, int *rowblkblock,
                          unsigned int **blkcoostylerowidx, int **blkcoostylerowidx_colstart,
                          int **blkcoostylerowidx_colstop, int rowA)
+try
 {
     clear_error();
     return prepare_entry(matrix, ptroffset1, ptroffset2, rowblkblock, blkcoostylerowidx, blkcoostylerowidx_colstart,
                          blkcoostylerowidx_colstop, rowA);
 }
+TSP_CATCH_INT("tilespmv_prepare_f64")
 int tilespmv_prepare_f32(const Tile_matrix_f32 *matrix, int *ptroffset1, int *ptroffset2, int *rowblkblock,
                          unsigned int **blkcoostylerowidx, int **blkcoostylerowidx_colstart,
                          int **blkcoostylerowidx_colstop, int rowA)
+try
 {
     clear_error();
     return prepare_entry(matrix, ptroffset1, ptroffset2, rowblkblock, blkcoostylerowidx, blkcoostylerowidx_colstart,
                          blkcoostylerowidx_colstop, rowA);
 }
+TSP_CATCH_INT("tilespmv_prepare_f32")
 
 void call_tilespmv_cuda_f64(char *filename, Tile_matrix_f64 *matrix, int *, int *, int, unsigned int *, int *, int *,
                             int rowA, int colA, int nnzA, int *, int *, double *, double, double *x, double *y, double *)
+try
 {
     clear_error();
     call_entry<Tile_matrix_f64, double>(filename, matrix, rowA, colA, nnzA, x, y);
 }
+TSP_CATCH_VOID("call_tilespmv_cuda_f64")
 void call_tilespmv_cuda_f32(char *filename, Tile_matrix_f32 *matrix, int *, int *, int, unsigned int *, int *, int *,
                             int rowA, int colA, int nnzA, int *, int *, float *, float, float *x, float *y, float *)
+try
 {
     clear_error();
     call_entry<Tile_matrix_f32, float>(filename, matrix, rowA, colA, nnzA, x, y);
 }
+TSP_CATCH_VOID("call_tilespmv_cuda_f32")
 
 int tilespmv_convert(int precision, int rowA, int colA, const int *rowptr, const int *colidx, const void *val,
                      unsigned flags, tilespmv_dmat **out)
+try
 {
     clear_error();
     return convert_entry(precision, rowA, colA, rowptr, colidx, val, flags, out);
 }
+TSP_CATCH_INT("tilespmv_convert")
 int tilespmv_dmat_upload_f64(const Tile_matrix_f64 *matrix, int rowA, int colA, tilespmv_dmat **out)
+try
 {
     clear_error();
     return dmat_upload<Tile_matrix_f64, double>(matrix, rowA, colA, out);
 }
+TSP_CATCH_INT("tilespmv_dmat_upload_f64")
 int tilespmv_dmat_upload_f32(const Tile_matrix_f32 *matrix, int rowA, int colA, tilespmv_dmat **out)
+try
 {
     clear_error();
     return dmat_upload<Tile_matrix_f32, float>(matrix, rowA, colA, out);
 }
+TSP_CATCH_INT("tilespmv_dmat_upload_f32")
 int tilespmv_dmat_export_f64(const tilespmv_dmat *dm, Tile_matrix_f64 *matrix)
+try
 {
     clear_error();
     return dmat_export<Tile_matrix_f64, double>(dm, matrix);
 }
+TSP_CATCH_INT("tilespmv_dmat_export_f64")
 int tilespmv_dmat_export_f32(const tilespmv_dmat *dm, Tile_matrix_f32 *matrix)
+try
 {
     clear_error();
     return dmat_export<Tile_matrix_f32, float>(dm, matrix);
 }
+TSP_CATCH_INT("tilespmv_dmat_export_f32")
 void tilespmv_dmat_destroy(tilespmv_dmat *dm) { delete dm; }
 
 int tilespmv_dmat_get_info(const tilespmv_dmat *dm, tilespmv_dmat_info *info)
+try
 {
     clear_error();
     if (!dm || !info)
@@ -1099,8 +1122,10 @@ int tilespmv_dmat_get_info(const tilespmv_dmat *dm, tilespmv_dmat_info *info)
     info->device_bytes = dm->device_bytes();
     return TILESPMV_OK;
 }
+TSP_CATCH_INT("tilespmv_dmat_get_info")
 
 int tilespmv_plan_create(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, tilespmv_plan **out)
+try
 {
     clear_error();
     if (!dm || !out)
@@ -1121,7 +1146,9 @@ int tilespmv_plan_create(const tilespmv_dmat *dm, const tilespmv_plan_options *o
     *out = P;
     return TILESPMV_OK;
 }
+TSP_CATCH_INT("tilespmv_plan_create")
 int tilespmv_plan_save(const tilespmv_plan *plan, const char *path)
+try
 {
     clear_error();
     if (!plan || !path)
@@ -1131,7 +1158,9 @@ int tilespmv_plan_save(const tilespmv_plan *plan, const char *path)
     }
     return plan_save(plan, path);
 }
+TSP_CATCH_INT("tilespmv_plan_save")
 int tilespmv_plan_load(const char *path, tilespmv_plan **out)
+try
 {
     clear_error();
     if (!path || !out)
@@ -1142,9 +1171,11 @@ int tilespmv_plan_load(const char *path, tilespmv_plan **out)
     TSP_TRY(require_device());
     return plan_load(path, out);
 }
+TSP_CATCH_INT("tilespmv_plan_load")
 void tilespmv_plan_destroy(tilespmv_plan *plan) { delete plan; }
 
 int tilespmv_plan_spmv(tilespmv_plan *plan, const void *d_x, void *d_y, void *stream)
+try
 {
     clear_error();
     if (!plan || (!d_x && plan->colA) || (!d_y && plan->rowA))
@@ -1154,8 +1185,10 @@ int tilespmv_plan_spmv(tilespmv_plan *plan, const void *d_x, void *d_y, void *st
     }
     return plan_launch(plan, d_x, d_y, static_cast<cudaStream_t>(stream));
 }
+TSP_CATCH_INT("tilespmv_plan_spmv")
 
 int tilespmv_plan_spmv_host(tilespmv_plan *plan, const void *x, void *y)
+try
 {
     clear_error();
     if (!plan || (!x && plan->colA) || (!y && plan->rowA))
@@ -1176,8 +1209,10 @@ int tilespmv_plan_spmv_host(tilespmv_plan *plan, const void *x, void *y)
     TSP_CUDA(cudaStreamSynchronize(0));
     return TILESPMV_OK;
 }
+TSP_CATCH_INT("tilespmv_plan_spmv_host")
 
 int tilespmv_plan_spmv_host_batch(tilespmv_plan *plan, int nvec, const void *const *x, void *const *y)
+try
 {
     clear_error();
     if (!plan || nvec < 0 || (nvec > 0 && (!x || !y)))
@@ -1244,8 +1279,10 @@ int tilespmv_plan_spmv_host_batch(tilespmv_plan *plan, int nvec, const void *con
     TSP_CUDA(cudaStreamSynchronize(plan->s_out));
     return TILESPMV_OK;
 }
+TSP_CATCH_INT("tilespmv_plan_spmv_host_batch")
 
 int tilespmv_plan_iterate(tilespmv_plan *plan, void *d_xa, void *d_xb, int niters, void *stream)
+try
 {
     clear_error();
     if (!plan || niters < 0 || ((!d_xa || !d_xb) && plan->rowA))
@@ -1308,8 +1345,10 @@ int tilespmv_plan_iterate(tilespmv_plan *plan, void *d_xa, void *d_xb, int niter
     g_launches.fetch_add((int64_t)niters * info.launches_per_spmv, std::memory_order_relaxed);
     return TILESPMV_OK;
 }
+TSP_CATCH_INT("tilespmv_plan_iterate")
 
 int tilespmv_partition_rows(int precision, int rowA, const int *rowptr, int nparts, int *row_cuts)
+try
 {
     clear_error();
     if ((precision != TILESPMV_F64 && precision != TILESPMV_F32) || rowA < 0 || nparts < 1 || !row_cuts || (rowA > 0 && !rowptr))
@@ -1344,8 +1383,10 @@ int tilespmv_partition_rows(int precision, int rowA, const int *rowptr, int npar
     row_cuts[nparts] = rowA;
     return TILESPMV_OK;
 }
+TSP_CATCH_INT("tilespmv_partition_rows")
 
 int tilespmv_plan_set_peers(tilespmv_plan *plan, int npeers, void *const *peer_x, int64_t row_offset)
+try
 {
     clear_error();
     if (!plan || npeers < 0 || npeers > TSP_MAX_PEERS || (npeers > 0 && !peer_x))
@@ -1363,8 +1404,10 @@ int tilespmv_plan_set_peers(tilespmv_plan *plan, int npeers, void *const *peer_x
     }
     return TILESPMV_OK;
 }
+TSP_CATCH_INT("tilespmv_plan_set_peers")
 
 int tilespmv_plan_get_info(const tilespmv_plan *plan, tilespmv_plan_info *info)
+try
 {
     clear_error();
     if (!plan || !info)
@@ -1400,9 +1443,11 @@ int tilespmv_plan_get_info(const tilespmv_plan *plan, tilespmv_plan_info *info)
     info->csr_groups = plan->csr_groups;
     return TILESPMV_OK;
 }
+TSP_CATCH_INT("tilespmv_plan_get_info")
 
 int tilespmv_format_profile(const tilespmv_dmat *dm, const tilespmv_plan_options *opts, const void *d_x, void *d_y, int warmup, int iters,
                             double ms[9], int64_t nnz[9])
+try
 {
     clear_error();
     if (!dm || !ms || (!d_x && dm->colA) || (!d_y && dm->rowA))
@@ -1413,9 +1458,11 @@ int tilespmv_format_profile(const tilespmv_dmat *dm, const tilespmv_plan_options
     TSP_TRY(require_device());
     return format_profile_impl(dm, opts, d_x, d_y, warmup, iters, ms, nnz);
 }
+TSP_CATCH_INT("tilespmv_format_profile")
 
 int tilespmv_plan_time(tilespmv_plan *plan, const void *d_x, void *d_y, int warmup, int iters, void *stream,
                        double *ms_per_spmv)
+try
 {
     clear_error();
     if (!plan || !ms_per_spmv)
@@ -1425,18 +1472,23 @@ int tilespmv_plan_time(tilespmv_plan *plan, const void *d_x, void *d_y, int warm
     }
     return plan_time_impl(plan, d_x, d_y, warmup, iters, static_cast<cudaStream_t>(stream), ms_per_spmv);
 }
+TSP_CATCH_INT("tilespmv_plan_time")
 
 int tilespmv_mmio_allinone_f64(int *m, int *n, int *nnz, int *isSymmetric, int **csrRowPtr, int **csrColIdx,
                                double **csrVal, const char *filename)
+try
 {
     clear_error();
     return mmio_entry<double>(m, n, nnz, isSymmetric, csrRowPtr, csrColIdx, csrVal, filename);
 }
+TSP_CATCH_INT("tilespmv_mmio_allinone_f64")
 int tilespmv_mmio_allinone_f32(int *m, int *n, int *nnz, int *isSymmetric, int **csrRowPtr, int **csrColIdx,
                                float **csrVal, const char *filename)
+try
 {
     clear_error();
     return mmio_entry<float>(m, n, nnz, isSymmetric, csrRowPtr, csrColIdx, csrVal, filename);
 }
+TSP_CATCH_INT("tilespmv_mmio_allinone_f32")
 
 } // extern "C"

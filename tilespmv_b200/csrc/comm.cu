@@ -897,16 +897,21 @@ extern "C"
 {
 
 int tilespmv_comm_create(const char *name, int rank, int nranks, unsigned flags, tilespmv_comm **out)
+try
 {
     clear_error();
     return comm_create(name, rank, nranks, flags, out);
 }
+TSP_CATCH_INT("tilespmv_comm_create")
 void tilespmv_comm_destroy(tilespmv_comm *comm)
+try
 {
     clear_error();
     comm_destroy(comm);
 }
+TSP_CATCH_VOID("tilespmv_comm_destroy")
 int tilespmv_comm_barrier(tilespmv_comm *comm)
+try
 {
     clear_error();
     if (!comm)
@@ -916,14 +921,18 @@ int tilespmv_comm_barrier(tilespmv_comm *comm)
     }
     return comm_barrier(comm);
 }
+TSP_CATCH_INT("tilespmv_comm_barrier")
 
 int tilespmv_dist_create(tilespmv_comm *comm, const tilespmv_dmat *local_rows, const int64_t *row_cuts, const tilespmv_plan_options *opts,
                          unsigned flags, tilespmv_dist **out)
+try
 {
     clear_error();
     return dist_create(comm, local_rows, row_cuts, opts, flags, out);
 }
+TSP_CATCH_INT("tilespmv_dist_create")
 void tilespmv_dist_destroy(tilespmv_dist *dist)
+try
 {
     clear_error();
     if (!dist)
@@ -933,6 +942,7 @@ void tilespmv_dist_destroy(tilespmv_dist *dist)
         comm_barrier(dist->comm); // no peer still copies into (or out of) the block that is about to be freed
     delete dist;
 }
+TSP_CATCH_VOID("tilespmv_dist_destroy")
 
 // enqueue all iterations of one call on s_main (+ s_comm)
 static int iterate_enqueue(tilespmv_dist *d, int niters, int exchange)
@@ -951,6 +961,7 @@ static int iterate_enqueue(tilespmv_dist *d, int niters, int exchange)
 }
 
 int tilespmv_dist_iterate(tilespmv_dist *dist, const void *d_x0, int niters, int exchange, void *stream)
+try
 {
     clear_error();
     if (!dist || niters < 0 || exchange < TILESPMV_EXCHANGE_NCCL || exchange > TILESPMV_EXCHANGE_HALO)
@@ -1037,6 +1048,7 @@ int tilespmv_dist_iterate(tilespmv_dist *dist, const void *d_x0, int niters, int
     TSP_CUDA(cudaStreamWaitEvent(su, d->ev_done, 0));
     return TILESPMV_OK;
 }
+TSP_CATCH_INT("tilespmv_dist_iterate")
 
 void *tilespmv_dist_x(tilespmv_dist *dist)
 {
@@ -1051,6 +1063,7 @@ tilespmv_plan *tilespmv_dist_plan(tilespmv_dist *dist)
 }
 
 int tilespmv_dist_sync(tilespmv_dist *dist, void *stream)
+try
 {
     clear_error();
     if (!dist)
@@ -1078,8 +1091,10 @@ int tilespmv_dist_sync(tilespmv_dist *dist, void *stream)
     }
     return TILESPMV_OK;
 }
+TSP_CATCH_INT("tilespmv_dist_sync")
 
 int tilespmv_dist_get_info(const tilespmv_dist *dist, tilespmv_dist_info *info)
+try
 {
     clear_error();
     if (!dist || !info)
@@ -1103,5 +1118,6 @@ int tilespmv_dist_get_info(const tilespmv_dist *dist, tilespmv_dist_info *info)
     info->device_bytes = (int64_t)dist->block.bytes + dist->plan->device_bytes();
     return TILESPMV_OK;
 }
+TSP_CATCH_INT("tilespmv_dist_get_info")
 
 } // extern "C"

@@ -1,5 +1,7 @@
 // common.cuh -- shared host/device helpers of libtilespmv_b200 (sm_100a only).
 #pragma once
+#include <exception>
+#include <new>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -67,6 +69,35 @@ struct Status
             return TILESPMV_ERR_CUDA;                                                           \
         }                                                                                       \
     } while (0)
+
+// No C++ exception may cross the C-ABI: every extern "C" entry with a body of its own is a function-try-block that ends in
+// one of these handlers (std::bad_alloc from a host vector sized by the matrix, std::length_error, ...).  A void entry
+// reports through tilespmv_last_error() like its other failures.
+#define TSP_CATCH_INT(name)                                                                     \
+    catch (const std::bad_alloc &)                                                              \
+    {                                                                                           \
+        ::tsp::set_error("%s: out of host memory", name);                                       \
+        return TILESPMV_ERR_ALLOC;                                                              \
+    }                                                                                           \
+    catch (const std::exception &e__)                                                           \
+    {                                                                                           \
+        ::tsp::set_error("%s: %s", name, e__.what());                                           \
+        return TILESPMV_ERR_INVALID;                                                            \
+    }                                                                                           \
+    catch (...)                                                                                 \
+    {                                                                                           \
+        ::tsp::set_error("%s: unknown C++ exception", name);                                    \
+        return TILESPMV_ERR_INVALID;                                                            \
+    }
+#define TSP_CATCH_VOID(name)                                                                    \
+    catch (const std::exception &e__)                                                           \
+    {                                                                                           \
+        ::tsp::set_error("%s: %s", name, e__.what());                                           \
+    }                                                                                           \
+    catch (...)                                                                                 \
+    {                                                                                           \
+        ::tsp::set_error("%s: unknown C++ exception", name);                                    \
+    }
 
 // The product has no CPU fallback: every entry point that computes fails loudly without a GPU.
 int require_device();

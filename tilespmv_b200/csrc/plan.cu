@@ -1878,8 +1878,28 @@ int plan_load(const char *path, tilespmv_plan **out)
                   h.smem_optin, sms, smem_optin);
         return TILESPMV_ERR_UNSUPPORTED;
     }
-    std::vector<unsigned char> buf((size_t)h.payload_bytes);
-    const bool read_ok = fread(buf.data(), 1, buf.size(), f) == buf.size();
+    // the payload size comes from the file: believe it only if the file really is that long (a damaged header must end
+    // in TILESPMV_ERR_IO, not in an allocation of 2^60 bytes)
+    long file_end = -1;
+    if (fseek(f, 0, SEEK_END) == 0)
+        file_end = ftell(f);
+    std::vector<unsigned char> buf;
+    bool read_ok = file_end >= (long)sizeof(h) && (uint64_t)(file_end - (long)sizeof(h)) == h.payload_bytes &&
+                   fseek(f, (long)sizeof(h), SEEK_SET) == 0;
+    if (read_ok)
+    {
+        try
+        {
+            buf.resize((size_t)h.payload_bytes);
+        }
+        catch (const std::exception &)
+        {
+            fclose(f);
+            set_error("plan_load: out of host memory for the %llu bytes of %s", (unsigned long long)h.payload_bytes, path);
+            return TILESPMV_ERR_ALLOC;
+        }
+        read_ok = fread(buf.data(), 1, buf.size(), f) == buf.size();
+    }
     fclose(f);
     if (!read_ok || fnv1a(buf.data(), buf.size(), 1469598103934665603ull) != h.checksum)
     {
@@ -1899,8 +1919,11 @@ int plan_load(const char *path, tilespmv_plan **out)
             return fail((set_error("plan_load: %s is truncated", path), TILESPMV_ERR_IO));
         memcpy(&r, buf.data() + pos, sizeof(r));
         pos += sizeof(r);
-        if (pos + r.bytes_stream + r.bytes_desc + r.bytes_head + r.bytes_split > buf.size())
-            return fail((set_error("plan_load: %s is truncated", path), TILESPMV_ERR_IO));
+        const uint64_t left = (uint64_t)(buf.size() - pos); // every size is checked on its own: the sum cannot wrap
+        if (r.bytes_stream > left || r.bytes_desc > left || r.bytes_head > left || r.bytes_split > left ||
+            r.bytes_stream + r.bytes_desc + r.bytes_head + r.bytes_split > left || r.nslots < 0 || r.nsplit < 0 ||
+            (r.precision != 4 && r.precision != 8) || r.bytes_split != (uint64_t)r.nsplit * 4 * sizeof(int))
+            return fail((set_error("plan_load: %s is truncated or inconsistent", path), TILESPMV_ERR_IO));
         tilespmv_plan *Q = new (std::nothrow) tilespmv_plan();
         if (!Q)
             return fail(TILESPMV_ERR_ALLOC);
@@ -1958,7 +1981,8 @@ int plan_load(const char *path, tilespmv_plan **out)
         if (rc != TILESPMV_OK)
             return fail(rc);
     }
-    TSP_CUDA(cudaDeviceSynchronize());
+    if (cudaDeviceSynchronize() != cudaSuccess)
+        return fail((set_error("plan_load: %s", cudaGetErrorString(cudaGetLastError())), TILESPMV_ERR_CUDA));
     *out = root;
     return TILESPMV_OK;
 }
