@@ -208,6 +208,17 @@ def _quiet_stdout():
     return Q()
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_sample(wl, args):
     """A bounded sample of the workload the CPU path finishes in a fraction of a second per call."""
     from tilespmv_b200 import generators as g
@@ -263,7 +274,7 @@ def cpu_baseline(wl, args, steps=3, warm=0, budget_s=150.0):
             "sample": f"{what}, tilespmv_cpu whole call, best of {len(timed)}; Tile_matrix built by the oracle port in {t_conv:.1f}s "
                       f"with {ora.threads()} threads (untimed)",
             "ms_per_call": best, "mean_ms_per_call": mean, "calls": len(timed), "nnz_sample": nnz,
-            "host_threads_available": ora.threads()}
+            "host_threads_available": ora.threads(), "cpu_model": cpu_model()}
 
 
 def conversion_baseline(gpu=True):
