@@ -234,7 +234,9 @@ def test_back_to_back_launches_see_the_previous_result(name):
     m, n, rp, ci, v = BIG_CASES[name]()
     assert m == n
     dm = api.DeviceTileMatrix.from_csr(m, n, rp, ci, v * (1.0 / 64))
-    for kw in ({}, {"xpanel_bytes": 64 * 1024}):
+    # default plan, x panels (accumulating sub-plans), tiny staging budgets (rows cut into pieces: the fix-up kernels are
+    # links of the chain too)
+    for kw in ({}, {"xpanel_bytes": 64 * 1024}, {"chunk_bytes": 2560, "xstage_bytes": 128}):
         plan = api.Plan(dm, **kw)
         x0 = torch.from_numpy(np.random.default_rng(5).uniform(-1, 1, n)).cuda()
         niters = 12

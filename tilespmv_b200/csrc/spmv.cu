@@ -1042,6 +1042,10 @@ __global__ void __launch_bounds__(128)
     split_fixup_kernel(const int4 *__restrict__ tab, long long nsplit, const T *__restrict__ scratch, T *__restrict__ y,
                        int npeers, long long row_offset, SpmvArgs<T> a)
 {
+    // a link of the programmatic-launch chain like the SpMV kernel itself: releases the next launch of the stream at once
+    // and waits for the kernel before it (whose partial sums it adds) -- no-ops when launched without the attribute
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long i = g >> 4;
     const int r = (int)(g & 15);
@@ -1070,6 +1074,8 @@ __global__ void __launch_bounds__(256)
                            long long row_offset, SpmvArgs<T> a)
 {
     __shared__ T part[16][TS + 1];
+    asm volatile("griddepcontrol.launch_dependents;"); // see split_fixup_kernel
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int4 e = tab[blockIdx.x]; // block row, first slot, #slots, rowlen
     const int r = threadIdx.x & 15, q = threadIdx.x >> 4;
     T s0 = 0, s1 = 0, s2 = 0, s3 = 0;
@@ -1257,16 +1263,18 @@ static int plan_launch_one(tilespmv_plan *P, const T *x, T *y, cudaStream_t s, i
     const int grid = P->grid; // fixed at plan time: the stream's lookahead lists depend on it
     static const bool no_plain = getenv("TILESPMV_NO_PLAIN_EPILOGUE") != nullptr; // A/B switch, read once
     const bool plain = npeers == 0 && !a.accumulate && !no_plain;
+    bool pdl = false;
     {
         void *args[] = {(void *)&a};
         // programmatic dependent launch (see the top of the kernel): this launch may begin while the previous kernel of
         // the stream drains; the kernel itself waits (griddepcontrol.wait) before it touches x, y or the scratch.  Only a
         // kernel-to-kernel edge of the same stream is relaxed; copies, events and kernels launched without the attribute
-        // (the fix-up kernels below, the flag kernels of comm.cu, the caller's own kernels) keep the full stream order.
+        // (the flag kernels of comm.cu, the caller's own kernels) keep the full stream order.  The fix-up kernels below are
+        // links of the same chain: released by this kernel's first instruction, they wait for it before they read a sum.
         // Stream captures keep the attribute (the graph gets a programmatic edge: tilespmv_plan_iterate 21.1 -> 19.8 us per
         // iteration on config 1).  A/B switches: TILESPMV_NO_PDL=1 (never), TILESPMV_NO_PDL_IN_GRAPHS=1 (not while capturing).
         static const int pdl_mode = getenv("TILESPMV_NO_PDL") ? 0 : (getenv("TILESPMV_NO_PDL_IN_GRAPHS") ? 1 : 2);
-        bool pdl = pdl_mode != 0;
+        pdl = pdl_mode != 0;
         if (pdl_mode == 1)
         {
             cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -1291,14 +1299,36 @@ static int plan_launch_one(tilespmv_plan *P, const T *x, T *y, cudaStream_t s, i
             return TILESPMV_ERR_CUDA;
         }
     }
+    // the fix-up kernels are links of the same chain (TILESPMV_NO_PDL_FIXUP=1: plain launches, the A/B switch)
+    static const bool chain_fixup = getenv("TILESPMV_NO_PDL_FIXUP") == nullptr;
+    auto launch_fixup = [&](auto kernel, unsigned fgrid, unsigned fblock, auto... kargs) -> int {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(fgrid);
+        cfg.blockDim = dim3(fblock);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = (pdl && chain_fixup) ? 1 : 0;
+        cudaError_t err = cudaLaunchKernelEx(&cfg, kernel, kargs...);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (err != cudaSuccess)
+        {
+            set_error("launch of a split fix-up kernel failed: %s", cudaGetErrorString(err));
+            return TILESPMV_ERR_CUDA;
+        }
+        return TILESPMV_OK;
+    };
     if (P->nsplit > P->nsplit_small)
-        TSP_LAUNCH((split_fixup_big_kernel<T>), (unsigned)(P->nsplit - P->nsplit_small), 256, 0, s,
-                   P->split_tab.as<int4>() + P->nsplit_small, P->scratch.as<T>(), y, npeers, (long long)row_offset, a);
+        TSP_TRY(launch_fixup(split_fixup_big_kernel<T>, (unsigned)(P->nsplit - P->nsplit_small), 256u,
+                             (const int4 *)(P->split_tab.as<int4>() + P->nsplit_small), (const T *)P->scratch.as<T>(), y, npeers,
+                             (long long)row_offset, a));
     if (P->nsplit_small > 0)
     {
         const long long threads = P->nsplit_small * TS;
-        TSP_LAUNCH((split_fixup_kernel<T>), grid_for((size_t)threads, 128), 128, 0, s, P->split_tab.as<int4>(), (long long)P->nsplit_small,
-                   P->scratch.as<T>(), y, npeers, (long long)row_offset, a);
+        TSP_TRY(launch_fixup(split_fixup_kernel<T>, grid_for((size_t)threads, 128), 128u, (const int4 *)P->split_tab.as<int4>(),
+                             (long long)P->nsplit_small, (const T *)P->scratch.as<T>(), y, npeers, (long long)row_offset, a));
     }
     return TILESPMV_OK;
 }
